@@ -1,0 +1,196 @@
+/*
+ * massiv_b200.h — C ABI of libmassiv_b200.so: massiv's stencil / windowed-load hot path on B200.
+ *
+ * The reference (lehins/massiv 1.0.5.0) is pure Haskell with no FFI on this path; the seam this
+ * library replaces is `compute` of an `Array DW` produced by mapStencil/applyStencil, i.e. the
+ * per-element callback loader
+ *     iterArrayLinearST_ :: Scheduler s () -> Array DW ix e -> (Int -> e -> ST s ()) -> ST s ()
+ *     (massiv/src/Data/Massiv/Core/Common.hs:420-426; instances Array/Delayed/Windowed.hs:231,350,364).
+ * A Haskell shim (haskell/Data/Massiv/Array/Stencil/B200.hs, bindings shown in INTEGRATION.md)
+ * reifies the built-in stencil constructors into `mb_stencil_desc` and calls the entry points
+ * below with `foreign import ccall safe` on Storable (`S`) arrays.  Paths in the comments are
+ * relative to /root/reference/massiv/src/Data/Massiv/.
+ *
+ * Conventions
+ *   - arrays are dense row-major, last index fastest, no pitch (Core/Index/Internal.hs:584-595);
+ *     dims[0] is the OUTERMOST dimension; native-endian elements; element sizes follow
+ *     Storable.sizeOf (Bool is 4 bytes, Array/Manifest/Storable.hs:71-77).
+ *   - every function returns an mb_status; no C++ exception crosses the boundary;
+ *     mb_last_error(ctx) gives the text.  The shim maps MB_ERR_INDEX_ZERO to IndexZeroException,
+ *     MB_ERR_SIZE_MISMATCH to SizeMismatchException (Core/Index/Internal.hs:1136-1142).
+ *   - re-entrant: a context serialises its own calls with a mutex and sets its device on every
+ *     entry, so it may be called from any OS thread (`compute` is unsafePerformIO and safe FFI calls
+ *     migrate between OS threads, Array/Manifest/Internal.hs:66).
+ *   - there is NO CPU fallback: every entry point that computes fails with MB_ERR_CUDA when no
+ *     device is usable.
+ *   - floating point: one IEEE-754 round-to-nearest operation per reference operation, never
+ *     contracted into FMA, in the reference's accumulation order: results
+ *     are bit-identical to massiv's for finite and non-finite inputs (NaN payloads excepted).
+ *     MB_FLAG_ASSUME_FINITE lets CONV/CORR/TAPS/MAG2 skip zero coefficients, which is
+ *     bit-identical for finite inputs only (a skipped 0*Inf would have produced NaN).
+ */
+#ifndef MASSIV_B200_H
+#define MASSIV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_MAX_RANK 5
+#define MB_VERSION 100 /* 0.1.0 */
+
+typedef enum mb_status {
+  MB_OK = 0,
+  MB_ERR_INVALID_DESC = 1,  /* malformed descriptor / arguments                              */
+  MB_ERR_SIZE_MISMATCH = 2, /* iterate on a stencil whose output size differs from its input  */
+  MB_ERR_INDEX_ZERO = 3,    /* non-Fill border evaluated on a zero extent: IndexZeroException
+                               (Core/Index/Internal.hs:1031)                                   */
+  MB_ERR_UNSUPPORTED = 4,   /* element type / kind combination the reference's classes forbid */
+  MB_ERR_CUDA = 5,
+  MB_ERR_NCCL = 6,
+  MB_ERR_OOM = 7
+} mb_status;
+
+/* Storable element types */
+typedef enum mb_elem {
+  MB_U8 = 0, MB_I8, MB_U16, MB_I16, MB_U32, MB_I32, MB_U64, MB_I64, MB_F32, MB_F64, MB_BOOL32
+} mb_elem;
+
+/* the stencil constructors the device path recognises (closures cannot run on the device) */
+typedef enum mb_kind {
+  MB_ID = 0,   /* idStencil                                   Array/Stencil.hs:269            */
+  MB_SUM,      /* sumStencil      ((0 + x0) + x1) + ...        Array/Stencil.hs:425-427        */
+  MB_PRODUCT,  /* productStencil                               Array/Stencil.hs:454-456        */
+  MB_AVG,      /* avgStencil      sum / fromIntegral n         Array/Stencil.hs:479-481        */
+  MB_MAX,      /* maxStencil      from minBound                Array/Stencil.hs:368-370        */
+  MB_MIN,      /* minStencil      from maxBound                Array/Stencil.hs:401-403        */
+  MB_CONV,     /* makeConvolutionStencilFromKernel             Array/Stencil/Convolution.hs:64-80   */
+  MB_CORR,     /* makeCorrelationStencilFromKernel             Array/Stencil/Convolution.hs:107-121 */
+  MB_TAPS,     /* make(Unsafe){Convolution,Correlation}Stencil closure form lowered to an ordered
+                  tap list: acc = src[ix + off_t] * k_t + acc  Array/Stencil/Convolution.hs:44-57, 89-100 */
+  MB_LIFE,     /* Game-of-Life rule on Word8                   massiv-examples/GameOfLife/app/GameOfLife.hs:15-36 */
+  MB_MAG2      /* sqrt (fmap (^2) a + fmap (^2) b), a,b FromKernel stencils of one size (Sobel)
+                  Array/Stencil/Internal.hs:105-146; massiv-bench/src/Data/Massiv/Bench/Sobel.hs:39-44 */
+} mb_kind;
+
+/* Border (Core/Index.hs:159-195) resolved by handleBorderIndex (Core/Index.hs:236-253) */
+typedef enum mb_border { MB_FILL = 0, MB_WRAP, MB_EDGE, MB_REFLECT, MB_CONTINUE } mb_border;
+
+#define MB_FLAG_MAG2_CORR 1u     /* MAG2 sub-stencils are correlations                         */
+#define MB_FLAG_ASSUME_FINITE 2u /* inputs are finite: zero coefficients may be skipped        */
+
+/*
+ * One reified  applyStencil (Padding pad_lo pad_hi border) stencil  [computeWithStride stride].
+ * mapStencil = pad_lo := center, pad_hi := size - (center + 1)   (Array/Stencil.hs:76-86, 173-179).
+ * `center` is stencilCenter: 0 for the fold stencils, size-1-(size `quot` 2) for CONV/MAG2,
+ * size `div` 2 for CORR, (1,1) for LIFE, caller-chosen for TAPS; it is validated.
+ */
+typedef struct mb_stencil_desc {
+  int32_t kind;                  /* mb_kind   */
+  int32_t elem;                  /* mb_elem   */
+  int32_t rank;                  /* 1..MB_MAX_RANK */
+  int32_t border;                /* mb_border */
+  int64_t size[MB_MAX_RANK];     /* stencilSize, outermost first                               */
+  int64_t center[MB_MAX_RANK];   /* stencilCenter                                              */
+  int64_t pad_lo[MB_MAX_RANK];   /* paddingFromOrigin                                          */
+  int64_t pad_hi[MB_MAX_RANK];   /* paddingFromBottom                                          */
+  int64_t stride[MB_MAX_RANK];   /* Stride (Core/Index/Stride.hs:52-61); 1 = plain compute     */
+  uint8_t fill[8];               /* Fill element (native-endian, first sizeof(elem) bytes)     */
+  const void *coeffs;            /* CONV/CORR/MAG2: prod(size) elements row-major; TAPS: ntaps */
+  const void *coeffs2;           /* MAG2: second kernel                                        */
+  int64_t ntaps;                 /* TAPS                                                       */
+  const int64_t *tap_offsets;    /* TAPS: ntaps*rank source offsets in application order       */
+  uint32_t flags;
+  uint32_t reserved;
+} mb_stencil_desc;
+
+typedef struct mb_ctx mb_ctx;
+
+/* ---- library / context -------------------------------------------------------------------- */
+int mb_version(void);
+const char *mb_status_string(int status);
+/* One context = one device + its streams, scratch and (optionally) one NCCL communicator.
+ * Replaces the scheduler hand-off of withMassivScheduler_ (Core/Loop.hs:468-474). */
+int mb_ctx_create(int device, mb_ctx **out);
+int mb_ctx_destroy(mb_ctx *ctx);
+const char *mb_last_error(mb_ctx *ctx);
+/* launch the context's kernels on an external cudaStream_t (NULL restores its own stream) */
+int mb_ctx_set_stream(mb_ctx *ctx, void *cuda_stream);
+int mb_sync(mb_ctx *ctx);
+/* tuning / test switches: "force_generic" (1 = always the generic kernel),
+ * "life_bitpack" (0 = byte-wise Life kernels only) */
+int mb_ctx_set_option(mb_ctx *ctx, const char *key, int64_t value);
+/* number of kernels of THIS library launched through the context so far */
+int64_t mb_launch_count(mb_ctx *ctx);
+/* name of the kernel family the last launch used ("generic", "tile2d", ...); for tests/bench */
+const char *mb_last_kernel(mb_ctx *ctx);
+
+/* ---- geometry (host only; usable without a GPU) -------------------------------------------- */
+int mb_elem_size(int elem);
+/* size arithmetic of applyStencil (Array/Stencil.hs:207-208) and strideSize (Stride.hs:102-105) */
+int mb_out_dims(const mb_stencil_desc *desc, const int64_t *in_dims, int64_t *out_dims);
+/* handleBorderIndex for one dimension; *is_fill = 1 when Fill yields the element instead */
+int mb_border_index(int border, int64_t extent, int64_t i, int64_t *repaired, int32_t *is_fill);
+
+/* ---- memory --------------------------------------------------------------------------------- */
+int mb_buf_alloc(mb_ctx *ctx, size_t bytes, void **dev_ptr);
+int mb_buf_free(mb_ctx *ctx, void *dev_ptr);
+int mb_upload(mb_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes);
+int mb_download(mb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+/* pinned host memory an `S` array can wrap (unsafeArrayFromForeignPtr0, Storable.hs:342-344) */
+int mb_host_alloc(mb_ctx *ctx, size_t bytes, void **host_ptr);
+int mb_host_free(mb_ctx *ctx, void *host_ptr);
+
+/* ---- compute: the replacement of `compute (applyStencil ...)` ------------------------------ */
+/* host -> host, the literal drop-in of computeAs S . applyStencil (Manifest/Internal.hs:65-126).
+ * host_out must hold prod(mb_out_dims) elements. */
+int mb_run(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *in_dims, const void *host_in,
+           void *host_out);
+/* device-resident form (asynchronous on the context stream) */
+int mb_run_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *in_dims, const void *dev_in,
+               void *dev_out);
+/* two-pass separable application: compute (mapStencil b second) . compute (mapStencil b first),
+ * the intermediate rounded to the element type — the massiv idiom for rank-1 factorable kernels.
+ * `first`/`second` must be same-size (mapStencil-shaped) descriptors of one elem/rank/border.
+ * Fused into one HBM round trip when the shapes allow, otherwise run as two passes through
+ * dev_tmp (may be NULL: scratch is taken from the context). */
+int mb_run_sep2_dev(mb_ctx *ctx, const mb_stencil_desc *first, const mb_stencil_desc *second,
+                    const int64_t *dims, const void *dev_in, void *dev_out, void *dev_tmp);
+int mb_run_sep2(mb_ctx *ctx, const mb_stencil_desc *first, const mb_stencil_desc *second,
+                const int64_t *dims, const void *host_in, void *host_out);
+
+/* iterateUntil (\n _ _ -> n >= n_steps-1) (\_ -> applyStencil ...)  (Manifest/Internal.hs:331-397):
+ * the stencil is applied n_steps (>= 1) times, double-buffered; output size must equal input size.
+ * dev_a holds the input; *result receives dev_a or dev_b, whichever holds the last array. */
+int mb_iterate_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, void *dev_a,
+                   void *dev_b, int64_t n_steps, void **result);
+int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in,
+               void *host_out, int64_t n_steps);
+
+/* ---- slab-sharded iteration across the GPUs of one box (one process per GPU) ---------------- */
+/* The global array is split along dims[0] into contiguous slabs, rank r owning planes
+ * [r*N/R, (r+1)*N/R).  Every step exchanges `halo` ghost planes with rank±1 (ncclSend/ncclRecv on
+ * a second stream, overlapped with the interior kernel).  The rendezvous itself (who is who, the
+ * unique id broadcast) is the host's job — torch.distributed in this repo. */
+#define MB_NCCL_ID_BYTES 128
+int mb_nccl_unique_id(uint8_t id[MB_NCCL_ID_BYTES]);
+int mb_shard_init(mb_ctx *ctx, int n_ranks, int rank, const uint8_t id[MB_NCCL_ID_BYTES]);
+int mb_shard_halo(const mb_stencil_desc *desc, int64_t *halo_lo, int64_t *halo_hi);
+/* local buffers dev_a/dev_b hold (halo_lo + local_dims[0] + halo_hi) planes: the rank's own
+ * planes at plane offset halo_lo.  global_dims[0] is the global outer extent (for the border at
+ * the two ends of the global array).  *result as in mb_iterate_dev. */
+int mb_iterate_sharded_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *global_dims,
+                           const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps,
+                           void **result);
+
+/* ---- timing helpers (CUDA events on the context stream; used by bench.py) ------------------- */
+int mb_timer_start(mb_ctx *ctx);
+int mb_timer_stop(mb_ctx *ctx, float *milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASSIV_B200_H */

@@ -1,0 +1,175 @@
+// Generic stencil kernel: any rank <= 5, any window, any stride/padding, all kinds and element
+// types.  One thread per output cell, every tap through the border rule — the direct restatement
+// of `warr`'s index function in applyStencil (Array/Stencil.hs:201-205).  It is the correctness
+// baseline the tiled kernels are tested against and the path for shapes they do not cover
+// (strides, ranks 1/4/5, odd windows, tiny arrays).  It is still a GPU kernel: there is no CPU path.
+#include "mb_arith.cuh"
+#include "mb_internal.h"
+
+namespace mb {
+
+struct GParams {
+  int rank, border, kind, bool_canon, skip_zero;
+  int64_t in_dims[MB_MAX_RANK], out_dims[MB_MAX_RANK], stride[MB_MAX_RANK], shift[MB_MAX_RANK];
+  int64_t ntaps, cell0, ncells, avg_n;
+  const int32_t *taps;
+  const void *c1, *c2;
+  unsigned long long fill_bits;
+};
+
+template <typename T>
+__device__ __forceinline__ T fetch(const GParams &P, const T *__restrict__ in, const int64_t *ix,
+                                   const int32_t *__restrict__ off, T fillv) {
+  int64_t lin = 0;
+#pragma unroll 1
+  for (int d = 0; d < P.rank; ++d) {
+    int64_t i = ix[d] + off[d];
+    if (!resolve_border(P.border, P.in_dims[d], i)) return fillv;  // Fill: ANY dim out => element
+    lin = lin * P.in_dims[d] + i;
+  }
+  T v = in[lin];
+  if (P.bool_canon) v = (T)(v != T(0));  // Storable Bool peek: (/= 0)
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *__restrict__ in, T *__restrict__ out) {
+  using A = Arith<T>;
+  using Acc = typename A::Acc;
+  T fillv;
+  {
+    unsigned long long b = P.fill_bits;
+    memcpy(&fillv, &b, sizeof(T));
+  }
+  const int r = P.rank;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < P.ncells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lin_out = P.cell0 + cell;
+    int64_t ix[MB_MAX_RANK];
+    {
+      int64_t rem = lin_out;
+#pragma unroll 1
+      for (int d = r - 1; d >= 0; --d) {
+        const int64_t j = rem % P.out_dims[d];
+        rem /= P.out_dims[d];
+        ix[d] = j * P.stride[d] + P.shift[d];  // Stencil.hs:200 + Stride.hs:110-120
+      }
+    }
+    const int32_t *taps = P.taps;
+    T res;
+    switch (P.kind) {
+      case MB_ID: res = fetch<T>(P, in, ix, taps, fillv); break;
+      case MB_SUM: case MB_AVG: {
+        Acc acc = A::from_count(0);
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        if (P.kind == MB_AVG) acc = A::div(acc, A::from_count(P.avg_n));
+        res = A::store(acc);
+        break;
+      }
+      case MB_PRODUCT: {
+        Acc acc = A::from_count(1);
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::mul(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        res = A::store(acc);
+        break;
+      }
+      case MB_MAX: {
+        T acc = P.bool_canon ? T(0) : Bounds<T>::lo();  // Bounded Bool: False..True
+        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv); acc = x > acc ? x : acc; }
+        res = acc;
+        break;
+      }
+      case MB_MIN: {
+        T acc = P.bool_canon ? T(1) : Bounds<T>::hi();
+        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv); acc = x < acc ? x : acc; }
+        res = acc;
+        break;
+      }
+      case MB_CONV: case MB_CORR: case MB_TAPS: {
+        const T *k = (const T *)P.c1;
+        Acc acc = A::from_count(0);
+        for (int64_t t = 0; t < P.ntaps; ++t) {
+          const Acc kv = A::load(k[t]);
+          if (P.skip_zero && A::is_zero(kv)) continue;
+          acc = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), acc);
+        }
+        res = A::store(acc);
+        break;
+      }
+      case MB_MAG2: {
+        const T *k1 = (const T *)P.c1, *k2 = (const T *)P.c2;
+        Acc a = A::from_count(0), b = A::from_count(0);
+        for (int64_t t = 0; t < P.ntaps; ++t) {
+          const Acc kv = A::load(k1[t]);
+          if (P.skip_zero && A::is_zero(kv)) continue;
+          a = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), a);
+        }
+        for (int64_t t = 0; t < P.ntaps; ++t) {
+          const Acc kv = A::load(k2[t]);
+          if (P.skip_zero && A::is_zero(kv)) continue;
+          b = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), b);
+        }
+        res = A::store(A::sqrt(A::add(A::mul(a, a), A::mul(b, b))));
+        break;
+      }
+      default: {  // MB_LIFE (T = uint8_t): GameOfLife.hs:15-36
+        unsigned n = 0;
+        for (int t = 0; t < 8; ++t) n += (unsigned)fetch<T>(P, in, ix, taps + t * r, fillv);
+        n &= 0xFFu;
+        const unsigned c = (unsigned)fetch<T>(P, in, ix, taps + 8 * r, fillv);
+        res = (T)(((c == 0 && n == 3) || (c == 1 && (n == 2 || n == 3))) ? 1 : 0);
+        break;
+      }
+    }
+    out[lin_out] = res;
+  }
+}
+
+template <typename T>
+static int launch_t(Ctx *c, const GParams &P, const void *in, void *out) {
+  const int block = 256;
+  int64_t blocks = (P.ncells + block - 1) / block;
+  const int64_t cap = (int64_t)c->num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  generic_kernel<T><<<(unsigned)blocks, block, 0, c->stream>>>(P, (const T *)in, (T *)out);
+  return check_cuda(c, cudaGetLastError(), "generic_kernel launch");
+}
+
+int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  const Plan &p = dp.p;
+  GParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.rank = p.rank; P.border = p.border; P.kind = p.kind;
+  P.bool_canon = p.elem == MB_BOOL32;
+  P.skip_zero = (p.flags & MB_FLAG_ASSUME_FINITE) != 0;
+  int64_t plane = 1;
+  for (int i = 0; i < p.rank; ++i) {
+    P.in_dims[i] = p.in_dims[i]; P.out_dims[i] = p.out_dims[i];
+    P.stride[i] = p.stride[i]; P.shift[i] = p.shift[i];
+    if (i > 0) plane *= p.out_dims[i];
+  }
+  P.ntaps = p.ntaps; P.avg_n = p.avg_n;
+  P.taps = dp.d_taps; P.c1 = dp.d_c1; P.c2 = dp.d_c2;
+  std::memcpy(&P.fill_bits, p.fill, 8);
+  int64_t o0 = 0, o1 = p.out_dims[0];
+  if (range) { o0 = range->o0; o1 = range->o1; }
+  P.cell0 = o0 * plane;
+  P.ncells = (o1 - o0) * plane;
+  if (P.ncells <= 0) return MB_OK;
+  c->launches++;
+  c->last_kernel = "generic";
+  switch (p.elem) {
+    case MB_U8: return launch_t<uint8_t>(c, P, d_in, d_out);
+    case MB_I8: return launch_t<int8_t>(c, P, d_in, d_out);
+    case MB_U16: return launch_t<uint16_t>(c, P, d_in, d_out);
+    case MB_I16: return launch_t<int16_t>(c, P, d_in, d_out);
+    case MB_U32: return launch_t<uint32_t>(c, P, d_in, d_out);
+    case MB_I32: case MB_BOOL32: return launch_t<int32_t>(c, P, d_in, d_out);
+    case MB_U64: return launch_t<uint64_t>(c, P, d_in, d_out);
+    case MB_I64: return launch_t<int64_t>(c, P, d_in, d_out);
+    case MB_F32: return launch_t<float>(c, P, d_in, d_out);
+    case MB_F64: return launch_t<double>(c, P, d_in, d_out);
+  }
+  return fail(c, MB_ERR_INVALID_DESC, "unknown element type");
+}
+
+}  // namespace mb

@@ -1,0 +1,442 @@
+// C-ABI entry points of libmassiv_b200.so (declared in include/massiv_b200.h): context, memory,
+// plan cache, kernel dispatch, run / iterate.  No torch types, no C++ exceptions across the boundary.
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+#include "mb_internal.h"
+
+namespace mb {
+
+int fail(Ctx *c, int status, const std::string &msg) {
+  if (c) c->err = msg;
+  return status;
+}
+
+int check_cuda(Ctx *c, cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return MB_OK;
+  std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  if (c) c->err = m;
+  return e == cudaErrorMemoryAllocation ? MB_ERR_OOM : MB_ERR_CUDA;
+}
+
+int ensure_scratch(Ctx *c, int slot, size_t bytes, void **ptr) {
+  if (bytes > c->scratch_bytes[slot]) {
+    if (c->scratch[slot]) {
+      MB_CUDA(c, cudaStreamSynchronize(c->stream));
+      MB_CUDA(c, cudaFree(c->scratch[slot]));
+      c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0;
+    }
+    MB_CUDA(c, cudaMalloc(&c->scratch[slot], bytes));
+    c->scratch_bytes[slot] = bytes;
+  }
+  *ptr = c->scratch[slot];
+  return MB_OK;
+}
+
+static void free_dev_plan(DevPlan *dp) {
+  if (dp->d_taps) cudaFree(dp->d_taps);
+  if (dp->d_c1) cudaFree(dp->d_c1);
+  if (dp->d_c2) cudaFree(dp->d_c2);
+  delete dp;
+}
+
+int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::shared_ptr<DevPlan> *out) {
+  Plan p;
+  std::string err;
+  int st = make_plan(d, in_dims, &p, &err);
+  if (st) return fail(c, st, err);
+  // cache key: every byte that determines the plan
+  std::string key;
+  key.append((const char *)d, offsetof(mb_stencil_desc, coeffs));
+  key.append((const char *)&d->ntaps, sizeof(d->ntaps));
+  key.append((const char *)&d->flags, sizeof(d->flags));
+  key.append((const char *)in_dims, sizeof(int64_t) * d->rank);
+  key.append((const char *)p.tap_off.data(), p.tap_off.size() * sizeof(int32_t));
+  key.append((const char *)p.c1.data(), p.c1.size());
+  key.append((const char *)p.c2.data(), p.c2.size());
+  auto it = c->plans.find(key);
+  if (it != c->plans.end()) { *out = it->second; return MB_OK; }
+  if (c->plans.size() > 256) c->plans.clear();  // bounded; shared_ptrs keep in-flight plans alive
+  std::shared_ptr<DevPlan> dp(new DevPlan(), free_dev_plan);
+  dp->p = std::move(p);
+  const Plan &q = dp->p;
+  if (!q.tap_off.empty()) {
+    MB_CUDA(c, cudaMalloc(&dp->d_taps, q.tap_off.size() * sizeof(int32_t)));
+    MB_CUDA(c, cudaMemcpyAsync(dp->d_taps, q.tap_off.data(), q.tap_off.size() * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!q.c1.empty()) {
+    MB_CUDA(c, cudaMalloc(&dp->d_c1, q.c1.size()));
+    MB_CUDA(c, cudaMemcpyAsync(dp->d_c1, q.c1.data(), q.c1.size(), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!q.c2.empty()) {
+    MB_CUDA(c, cudaMalloc(&dp->d_c2, q.c2.size()));
+    MB_CUDA(c, cudaMemcpyAsync(dp->d_c2, q.c2.data(), q.c2.size(), cudaMemcpyHostToDevice, c->stream));
+  }
+  // pageable-source async copies are staged before returning, so q's vectors may move freely
+  c->plans[key] = dp;
+  *out = dp;
+  return MB_OK;
+}
+
+// Kernel-family dispatch.  Order: most specialised first; each family answers -1 when the plan is
+// outside what it covers.  The generic kernel covers everything.
+int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  if (dp.p.out_elems == 0) return MB_OK;
+  if (!c->force_generic) {
+    int st = launch_life(c, dp, d_in, d_out);
+    if (st != -1) return st;
+    st = launch_tile2d(c, dp, d_in, d_out, range);
+    if (st != -1) return st;
+    st = launch_vol3d(c, dp, d_in, d_out, range);
+    if (st != -1) return st;
+  }
+  return launch_generic(c, dp, d_in, d_out, range);
+}
+
+struct Guard {
+  Ctx *c;
+  std::unique_lock<std::mutex> lk;
+  int st;
+  explicit Guard(mb_ctx *h) : c(h ? &h->c : nullptr), st(MB_OK) {
+    if (!c) { st = MB_ERR_INVALID_DESC; return; }
+    lk = std::unique_lock<std::mutex>(c->mu);
+    st = check_cuda(c, cudaSetDevice(c->device), "cudaSetDevice");  // no thread-local CUDA state assumed
+  }
+};
+
+static int copy_h2d(Ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!bytes) return MB_OK;
+  MB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return MB_OK;
+}
+static int copy_d2h(Ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!bytes) return MB_OK;
+  MB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return MB_OK;
+}
+
+static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t *dims, void *a, void *b,
+                              int64_t n_steps, void **result) {
+  if (n_steps < 1) return fail(c, MB_ERR_INVALID_DESC, "iterateUntil applies the step at least once");
+  std::shared_ptr<DevPlan> dp;
+  int st = get_dev_plan(c, desc, dims, &dp);
+  if (st) return st;
+  if (!dp->p.same_shape()) return fail(c, MB_ERR_SIZE_MISMATCH, "iterate needs output size == input size");
+  if (!c->force_generic) {
+    st = life_iterate(c, *dp, a, b, n_steps, result);
+    if (st != -1) return st;
+  }
+  void *cur = a, *nxt = b;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    st = launch_plan(c, *dp, cur, nxt, nullptr);
+    if (st) return st;
+    void *t = cur; cur = nxt; nxt = t;
+  }
+  *result = cur;
+  return MB_OK;
+}
+
+static int check_sep2(Ctx *c, const mb_stencil_desc *f, const mb_stencil_desc *s) {
+  if (!f || !s) return fail(c, MB_ERR_INVALID_DESC, "null descriptor");
+  if (f->elem != s->elem || f->rank != s->rank || f->border != s->border ||
+      std::memcmp(f->fill, s->fill, 8) != 0)
+    return fail(c, MB_ERR_INVALID_DESC, "separable passes must share element type, rank and border");
+  return MB_OK;
+}
+
+int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const void *d_in, void *d_out);
+
+static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_desc *s, const int64_t *dims,
+                           const void *d_in, void *d_out, void *d_tmp) {
+  int st = check_sep2(c, f, s);
+  if (st) return st;
+  std::shared_ptr<DevPlan> p1, p2;
+  if ((st = get_dev_plan(c, f, dims, &p1))) return st;
+  if ((st = get_dev_plan(c, s, dims, &p2))) return st;
+  if (!p1->p.same_shape() || !p2->p.same_shape())
+    return fail(c, MB_ERR_SIZE_MISMATCH, "separable passes must be mapStencil-shaped (same size in and out)");
+  if (!c->force_generic) {
+    st = run_sep2_fused(c, *p1, *p2, d_in, d_out);
+    if (st != -1) return st;
+  }
+  if (!d_tmp) {
+    if ((st = ensure_scratch(c, 2, (size_t)p1->p.out_elems * p1->p.esize, &d_tmp))) return st;
+  }
+  if ((st = launch_plan(c, *p1, d_in, d_tmp, nullptr))) return st;
+  return launch_plan(c, *p2, d_tmp, d_out, nullptr);
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_version(void) { return MB_VERSION; }
+
+const char *mb_status_string(int s) {
+  switch (s) {
+    case MB_OK: return "ok";
+    case MB_ERR_INVALID_DESC: return "invalid descriptor";
+    case MB_ERR_SIZE_MISMATCH: return "size mismatch";
+    case MB_ERR_INDEX_ZERO: return "index zero (empty dimension under a non-Fill border)";
+    case MB_ERR_UNSUPPORTED: return "unsupported element type / stencil kind";
+    case MB_ERR_CUDA: return "CUDA error";
+    case MB_ERR_NCCL: return "NCCL error";
+    case MB_ERR_OOM: return "out of device memory";
+  }
+  return "unknown status";
+}
+
+int mb_elem_size(int elem) {
+  switch (elem) {
+    case MB_U8: case MB_I8: return 1;
+    case MB_U16: case MB_I16: return 2;
+    case MB_U32: case MB_I32: case MB_F32: case MB_BOOL32: return 4;
+    case MB_U64: case MB_I64: case MB_F64: return 8;
+  }
+  return 0;
+}
+
+int mb_out_dims(const mb_stencil_desc *desc, const int64_t *in_dims, int64_t *out_dims) {
+  if (!desc || !in_dims || !out_dims) return MB_ERR_INVALID_DESC;
+  Plan p;
+  int st = plan_geometry(desc, in_dims, &p, nullptr);
+  if (st) return st;
+  for (int i = 0; i < desc->rank; ++i) out_dims[i] = p.out_dims[i];
+  return MB_OK;
+}
+
+int mb_border_index(int border, int64_t extent, int64_t i, int64_t *repaired, int32_t *is_fill) {
+  if (!repaired || !is_fill) return MB_ERR_INVALID_DESC;
+  return border_index(border, extent, i, repaired, is_fill);
+}
+
+int mb_ctx_create(int device, mb_ctx **out) {
+  if (!out) return MB_ERR_INVALID_DESC;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return MB_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return MB_ERR_CUDA;
+  mb_ctx *h = new (std::nothrow) mb_ctx();
+  if (!h) return MB_ERR_OOM;
+  Ctx *c = &h->c;
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return MB_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  if (const char *fg = std::getenv("MASSIV_B200_FORCE_GENERIC")) c->force_generic = std::atoi(fg);
+  *out = h;
+  return MB_OK;
+}
+
+int mb_ctx_destroy(mb_ctx *h) {
+  if (!h) return MB_OK;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  shard_destroy(c);
+  c->plans.clear();
+  for (int i = 0; i < 3; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  delete h;
+  return MB_OK;
+}
+
+const char *mb_last_error(mb_ctx *h) { return h ? h->c.err.c_str() : "null context"; }
+
+int mb_ctx_set_stream(mb_ctx *h, void *s) {
+  Guard g(h);
+  if (g.st) return g.st;
+  g.c->stream = s ? (cudaStream_t)s : g.c->own_stream;
+  return MB_OK;
+}
+
+int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
+  Guard g(h);
+  if (g.st) return g.st;
+  std::string k = key ? key : "";
+  if (k == "force_generic") g.c->force_generic = (int)value;
+  else if (k == "life_bitpack") g.c->life_bitpack = (int)value;
+  else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
+  return MB_OK;
+}
+
+int mb_sync(mb_ctx *h) {
+  Guard g(h);
+  if (g.st) return g.st;
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->stream));
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->comm_stream));
+  return MB_OK;
+}
+
+int64_t mb_launch_count(mb_ctx *h) { return h ? h->c.launches : 0; }
+const char *mb_last_kernel(mb_ctx *h) { return h ? h->c.last_kernel : "none"; }
+
+int mb_buf_alloc(mb_ctx *h, size_t bytes, void **p) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!p) return fail(g.c, MB_ERR_INVALID_DESC, "null out pointer");
+  *p = nullptr;
+  MB_CUDA(g.c, cudaMalloc(p, bytes ? bytes : 1));
+  return MB_OK;
+}
+
+int mb_buf_free(mb_ctx *h, void *p) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!p) return MB_OK;
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->stream));
+  MB_CUDA(g.c, cudaFree(p));
+  return MB_OK;
+}
+
+int mb_upload(mb_ctx *h, void *dst, const void *src, size_t bytes) {
+  Guard g(h);
+  if (g.st) return g.st;
+  int st = copy_h2d(g.c, dst, src, bytes);
+  if (st) return st;
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->stream));
+  return MB_OK;
+}
+
+int mb_download(mb_ctx *h, void *dst, const void *src, size_t bytes) {
+  Guard g(h);
+  if (g.st) return g.st;
+  int st = copy_d2h(g.c, dst, src, bytes);
+  if (st) return st;
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->stream));
+  return MB_OK;
+}
+
+int mb_host_alloc(mb_ctx *h, size_t bytes, void **p) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!p) return fail(g.c, MB_ERR_INVALID_DESC, "null out pointer");
+  MB_CUDA(g.c, cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+  return MB_OK;
+}
+
+int mb_host_free(mb_ctx *h, void *p) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (p) MB_CUDA(g.c, cudaFreeHost(p));
+  return MB_OK;
+}
+
+int mb_run_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *in_dims, const void *d_in, void *d_out) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!desc || !in_dims) return fail(g.c, MB_ERR_INVALID_DESC, "null argument");
+  std::shared_ptr<DevPlan> dp;
+  int st = get_dev_plan(g.c, desc, in_dims, &dp);
+  if (st) return st;
+  return launch_plan(g.c, *dp, d_in, d_out, nullptr);
+}
+
+int mb_run(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *in_dims, const void *host_in, void *host_out) {
+  Guard g(h);
+  if (g.st) return g.st;
+  Ctx *c = g.c;
+  if (!desc || !in_dims) return fail(c, MB_ERR_INVALID_DESC, "null argument");
+  std::shared_ptr<DevPlan> dp;
+  int st = get_dev_plan(c, desc, in_dims, &dp);
+  if (st) return st;
+  const size_t ib = (size_t)dp->p.in_elems * dp->p.esize, ob = (size_t)dp->p.out_elems * dp->p.esize;
+  void *d_in = nullptr, *d_out = nullptr;
+  if ((st = ensure_scratch(c, 0, ib ? ib : 1, &d_in))) return st;
+  if ((st = ensure_scratch(c, 1, ob ? ob : 1, &d_out))) return st;
+  if ((st = copy_h2d(c, d_in, host_in, ib))) return st;
+  if ((st = launch_plan(c, *dp, d_in, d_out, nullptr))) return st;
+  if ((st = copy_d2h(c, host_out, d_out, ob))) return st;
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+int mb_run_sep2_dev(mb_ctx *h, const mb_stencil_desc *f, const mb_stencil_desc *s, const int64_t *dims,
+                    const void *d_in, void *d_out, void *d_tmp) {
+  Guard g(h);
+  if (g.st) return g.st;
+  return sep2_dev_locked(g.c, f, s, dims, d_in, d_out, d_tmp);
+}
+
+int mb_run_sep2(mb_ctx *h, const mb_stencil_desc *f, const mb_stencil_desc *s, const int64_t *dims,
+                const void *host_in, void *host_out) {
+  Guard g(h);
+  if (g.st) return g.st;
+  Ctx *c = g.c;
+  int st = check_sep2(c, f, s);
+  if (st) return st;
+  size_t n = (size_t)mb_elem_size(f->elem);
+  for (int i = 0; i < f->rank; ++i) n *= (size_t)dims[i];
+  void *d_in = nullptr, *d_out = nullptr;
+  if ((st = ensure_scratch(c, 0, n ? n : 1, &d_in))) return st;
+  if ((st = ensure_scratch(c, 1, n ? n : 1, &d_out))) return st;
+  if ((st = copy_h2d(c, d_in, host_in, n))) return st;
+  if ((st = sep2_dev_locked(c, f, s, dims, d_in, d_out, nullptr))) return st;
+  if ((st = copy_d2h(c, host_out, d_out, n))) return st;
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+int mb_iterate_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, void *a, void *b,
+                   int64_t n_steps, void **result) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!desc || !dims || !result) return fail(g.c, MB_ERR_INVALID_DESC, "null argument");
+  return iterate_dev_locked(g.c, desc, dims, a, b, n_steps, result);
+}
+
+int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in, void *host_out,
+               int64_t n_steps) {
+  Guard g(h);
+  if (g.st) return g.st;
+  Ctx *c = g.c;
+  if (!desc || !dims) return fail(c, MB_ERR_INVALID_DESC, "null argument");
+  size_t n = (size_t)mb_elem_size(desc->elem);
+  for (int i = 0; i < desc->rank; ++i) n *= (size_t)dims[i];
+  void *a = nullptr, *b = nullptr, *res = nullptr;
+  int st;
+  if ((st = ensure_scratch(c, 0, n ? n : 1, &a))) return st;
+  if ((st = ensure_scratch(c, 1, n ? n : 1, &b))) return st;
+  if ((st = copy_h2d(c, a, host_in, n))) return st;
+  if ((st = iterate_dev_locked(c, desc, dims, a, b, n_steps, &res))) return st;
+  if ((st = copy_d2h(c, host_out, res, n))) return st;
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+int mb_timer_start(mb_ctx *h) {
+  Guard g(h);
+  if (g.st) return g.st;
+  MB_CUDA(g.c, cudaEventRecord(g.c->ev_start, g.c->stream));
+  return MB_OK;
+}
+
+int mb_timer_stop(mb_ctx *h, float *ms) {
+  Guard g(h);
+  if (g.st) return g.st;
+  MB_CUDA(g.c, cudaEventRecord(g.c->ev_stop, g.c->stream));
+  MB_CUDA(g.c, cudaEventSynchronize(g.c->ev_stop));
+  if (ms) MB_CUDA(g.c, cudaEventElapsedTime(ms, g.c->ev_start, g.c->ev_stop));
+  return MB_OK;
+}
+
+}  // extern "C"

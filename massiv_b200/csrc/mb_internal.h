@@ -1,0 +1,123 @@
+// Internal declarations shared by the translation units of libmassiv_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/massiv_b200.h"
+
+namespace mb {
+
+// Host-side normal form of one descriptor applied to one input shape.  Everything the kernels
+// need is derived here once: geometry (Array/Stencil.hs:197-217), the ordered tap list
+// (fold: Stencil.hs:298-302; FromKernel: Stencil/Convolution.hs:64-80,107-121) and the
+// coefficient bytes.
+struct Plan {
+  int kind = 0, elem = 0, rank = 0, border = 0;
+  uint32_t flags = 0;
+  int esize = 0;
+  int64_t in_dims[MB_MAX_RANK] = {0};
+  int64_t full_dims[MB_MAX_RANK] = {0};  // output extent before the stride is applied
+  int64_t out_dims[MB_MAX_RANK] = {0};   // strideSize of full_dims
+  int64_t stride[MB_MAX_RANK] = {0};
+  int64_t shift[MB_MAX_RANK] = {0};      // source index of output cell 0: centre - pad_lo
+  int64_t size[MB_MAX_RANK] = {0};       // tap window (desc.size)
+  int64_t geom[MB_MAX_RANK] = {0};       // size used for the geometry (AVG: max(size,1))
+  int64_t center[MB_MAX_RANK] = {0};
+  int64_t pad_lo[MB_MAX_RANK] = {0}, pad_hi[MB_MAX_RANK] = {0};
+  int64_t min_off[MB_MAX_RANK] = {0}, max_off[MB_MAX_RANK] = {0};
+  int64_t ntaps = 0;
+  int64_t avg_n = 0;                     // totalElem of desc.size
+  std::vector<int32_t> tap_off;          // ntaps * rank, application order
+  std::vector<uint8_t> c1, c2;           // ntaps coefficients each (elem bytes), may be empty
+  uint8_t fill[8] = {0};
+  int64_t in_elems = 0, out_elems = 0;
+  bool dense = false;                    // taps form the full [0,size) window (fold/conv/corr/mag2)
+  bool descending = false;               // dense taps visited with descending offsets (conv)
+  bool same_shape() const {
+    for (int i = 0; i < rank; ++i) if (out_dims[i] != in_dims[i]) return false;
+    return true;
+  }
+  bool unit_stride() const {
+    for (int i = 0; i < rank; ++i) if (stride[i] != 1) return false;
+    return true;
+  }
+};
+
+// validation + geometry only (no tap list): mb_out_dims
+int plan_geometry(const mb_stencil_desc *d, const int64_t *in_dims, Plan *p, std::string *err);
+// full plan
+int make_plan(const mb_stencil_desc *d, const int64_t *in_dims, Plan *p, std::string *err);
+int border_index(int border, int64_t k, int64_t i, int64_t *out, int32_t *is_fill);
+
+// A plan whose tap table / coefficients are resident on the device.
+struct DevPlan {
+  Plan p;
+  int32_t *d_taps = nullptr;
+  void *d_c1 = nullptr, *d_c2 = nullptr;
+};
+
+struct ShardState;  // mb_shard.cu
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_a = nullptr, ev_b = nullptr;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  const char *last_kernel = "none";
+  int num_sms = 148;
+  int force_generic = 0;   // mb_ctx_set_option("force_generic")
+  int life_bitpack = 1;    // mb_ctx_set_option("life_bitpack")
+  std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
+  // grow-only device scratch used by the host->host entry points and two-pass fallbacks
+  void *scratch[3] = {nullptr, nullptr, nullptr};
+  size_t scratch_bytes[3] = {0, 0, 0};
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+  ShardState *shard = nullptr;
+};
+
+int fail(Ctx *c, int status, const std::string &msg);
+int check_cuda(Ctx *c, cudaError_t e, const char *what);
+#define MB_CUDA(ctx, expr)                                          \
+  do {                                                              \
+    int _st = ::mb::check_cuda((ctx), (expr), #expr);               \
+    if (_st) return _st;                                            \
+  } while (0)
+
+int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::shared_ptr<DevPlan> *out);
+int ensure_scratch(Ctx *c, int slot, size_t bytes, void **ptr);
+
+// An output window along the outermost dimension: only output planes [o0, o1) are produced
+// (used by the slab-sharded path to peel boundary planes from the interior).
+struct OuterRange {
+  int64_t o0, o1;
+};
+
+// dispatcher: picks the kernel family for the plan and launches it on c->stream
+int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+
+// kernel families (each returns MB_OK, an error, or -1 for "not applicable, try the next one")
+int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+int launch_life(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out);
+// Life: many generations in one go (temporal blocking); returns -1 when not applicable
+int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_steps, void **result);
+
+void shard_destroy(Ctx *c);
+
+}  // namespace mb
+
+struct mb_ctx {
+  mb::Ctx c;
+};
