@@ -186,6 +186,12 @@ int mb_iterate_sharded_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64
                            const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps,
                            void **result);
 
+/* ---- device self-test (tests only) ----------------------------------------------------------- */
+/* compares the three-operation exact quotient avgStencil uses with the IEEE divide on `count`
+ * random / adversarial bit patterns of element type MB_F32 or MB_F64; *mismatches must be 0 */
+int mb_selftest_div(mb_ctx *ctx, int elem, int64_t n, uint64_t count, uint64_t seed,
+                    uint64_t *mismatches, uint64_t *first_bad_bits);
+
 /* ---- timing helpers (CUDA events on the context stream; used by bench.py) ------------------- */
 int mb_timer_start(mb_ctx *ctx);
 int mb_timer_stop(mb_ctx *ctx, float *milliseconds);

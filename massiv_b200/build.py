@@ -18,7 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libmassiv_b200.so")
 
-SOURCES = ["mb_plan.cpp", "mb_api.cu", "k_generic.cu", "k_tile2d.cu", "k_vol3d.cu", "k_life.cu", "mb_shard.cu"]
+SOURCES = ["mb_plan.cpp", "mb_api.cu", "k_generic.cu", "k_tile2d.cu", "k_vol3d.cu", "k_life.cu", "mb_shard.cu",
+           "k_selftest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: belt and braces — the kernels already use explicit *_rn intrinsics, which nvcc
 # never contracts; explicit fma() calls (exact-division helper) are unaffected by the flag.

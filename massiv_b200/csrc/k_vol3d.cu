@@ -1,4 +1,390 @@
+// Rank-3 3x3x3 convolution / correlation stencils — the iterated heat / Laplacian step
+// (reference: loadWithIxN, Array/Delayed/Windowed.hs:432-474: one job per outer page, each page a
+// rank-2 windowed load; FromKernel arithmetic, Array/Stencil/Convolution.hs:64-80, 107-121).
+//
+// Design (B200): 2.5-D streaming.  A persistent CTA owns a (TY x TX) column of the grid and marches
+// along the outermost dimension.  Every source plane tile (with its one-cell halo) is brought into
+// shared memory exactly once by a 3-D TMA box load into an S-deep mbarrier ring that runs several
+// planes ahead of the arithmetic; TMA's out-of-range zero fill is the `Fill 0` border in all three
+// dimensions.  Planes z-1 and z live in registers (the window slides along z), so one plane is read
+// from HBM once per pass and the kernel moves the algorithmic 2 x sizeof(e) bytes per cell.
+//   STAR7   : the seven face/centre coefficients are the only non-zero ones and the caller promised
+//             finite inputs (MB_FLAG_ASSUME_FINITE): 7 multiply + 7 add per cell, in kernel order.
+//   DENSE27 : any 3x3x3 kernel, all 27 taps (zero coefficients included — strict NaN/Inf semantics).
+// Tiles whose box leaves the array under a non-zero border are filled through the border rule by a
+// peeled path; the arithmetic loop is the same for every tile.
+#include "mb_arith.cuh"
 #include "mb_internal.h"
+#include "mb_tma.cuh"
+
 namespace mb {
-int launch_vol3d(Ctx *, const DevPlan &, const void *, void *, const OuterRange *) { return -1; }
+
+enum { V3_STAR7 = 0, V3_DENSE27 = 1 };
+
+struct V3Params {
+  int in_d, in_h, in_w, out_d, out_h, out_w;
+  int sz, sy, sx;  // source index of the window centre for output (0,0,0)
+  int z0, z1;      // output planes produced
+  int tiles_x, tiles_y, zc, nitems;
+  int border, use_tma, zero_fill_ok, vec_store;
+  unsigned long long fill_bits;
+};
+
+template <typename T> struct Coef27 {
+  T k[27];
+};
+
+template <typename T, int MODE> struct V3Cfg {
+  static constexpr int V = 16 / (int)sizeof(T);
+  static constexpr int TX = 32 * V;
+  static constexpr int R = MODE == V3_STAR7 ? 4 : 2;
+  static constexpr int TY = 8 * R;
+  static constexpr int BW = TX + 2 * V;  // left/right halo padded to a whole vector: rows stay 16 B aligned
+  static constexpr int BH = TY + 2;
+  static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
+  static constexpr int S = MODE == V3_STAR7 ? 5 : 6;
+  static constexpr int SMEM = S * STAGE + 64;
+};
+
+template <typename T> __device__ __forceinline__ void lds_vec(T *dst, const T *src) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const uint4 q = *reinterpret_cast<const uint4 *>(src);
+  T tmp[V];
+  memcpy(tmp, &q, 16);
+#pragma unroll
+  for (int v = 0; v < V; ++v) dst[v] = tmp[v];
 }
+
+template <typename T, int MODE, bool REV>
+__global__ void __launch_bounds__(256, MODE == V3_STAR7 ? 2 : 1)
+vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const Coef27<T> K,
+             const T *__restrict__ in, T *__restrict__ out) {
+  using C = V3Cfg<T, MODE>;
+  using A = Arith<T>;
+  constexpr int V = C::V, R = C::R, S = C::S;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * C::STAGE);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    if (P.use_tma) tma_prefetch_desc(&tmap);
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int my_items = (P.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_geom = [&](int it, int &oz0, int &nz, int &oy0, int &ox0) {
+    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = t % P.tiles_x, rest = t / P.tiles_x;
+    const int ty = rest % P.tiles_y, zi = rest / P.tiles_y;
+    oz0 = P.z0 + zi * P.zc;
+    nz = min(P.zc, P.z1 - oz0);
+    oy0 = ty * C::TY;
+    ox0 = tx * C::TX;
+  };
+  // may the plane box be fetched by TMA (out-of-range cells unused, or zero IS the border)?
+  auto tma_ok = [&](int zsrc, int oy0, int ox0) -> bool {
+    if (!P.use_tma) return false;
+    if (P.zero_fill_ok) return true;
+    const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - 1;
+    const int th = min(C::TY, P.out_h - oy0), tw = min(C::TX, P.out_w - ox0);
+    return zsrc >= 0 && zsrc < P.in_d && y0 >= 0 && x0 >= 0 && y0 + th + 2 <= P.in_h && x0 + tw + 2 <= P.in_w;
+  };
+
+  // ---- producer state (thread 0): loads are numbered globally, stage = number % S ----
+  int p_it = 0, p_pl = 0, issued = 0, released = 0;
+  int total_loads = 0;
+  for (int it = 0; it < my_items; ++it) {
+    int a, nz, b, c;
+    item_geom(it, a, nz, b, c);
+    total_loads += nz + 2;
+  }
+  auto issue_next = [&]() {  // thread 0 only
+    int oz0, nz, oy0, ox0;
+    item_geom(p_it, oz0, nz, oy0, ox0);
+    const int zsrc = oz0 + P.sz - 1 + p_pl;
+    const int s = issued % S;
+    if (tma_ok(zsrc, oy0, ox0)) {
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
+      tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], ox0 + P.sx - V, oy0 + P.sy - 1, zsrc);
+    }
+    ++issued;
+    if (++p_pl == nz + 2) { p_pl = 0; ++p_it; }
+  };
+  if (tid == 0) {
+    while (issued < total_loads && issued < released + S) issue_next();
+  }
+
+  T fillv;
+  {
+    unsigned long long b = P.fill_bits;
+    memcpy(&fillv, &b, sizeof(T));
+  }
+  uint32_t phase = 0;
+  // consumer side of one load: wait for the TMA, or fill the stage through the border rule
+  auto acquire = [&](int L, int zsrc, int oy0, int ox0) {
+    const int s = L % S;
+    if (tma_ok(zsrc, oy0, ox0)) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
+      const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - V;
+      int gz = zsrc;
+      const bool zin = resolve_border32(P.border, P.in_d, gz);
+      for (int e = tid; e < C::BW * C::BH; e += 256) {
+        const int r = e / C::BW, c = e - r * C::BW;
+        int gy = y0 + r, gx = x0 + c;
+        T v = fillv;
+        if (zin && resolve_border32(P.border, P.in_h, gy) && resolve_border32(P.border, P.in_w, gx))
+          v = in[((size_t)gz * P.in_h + gy) * P.in_w + gx];
+        sm[e] = v;
+      }
+      fence_proxy_async();
+      __syncthreads();
+    }
+  };
+
+  const int lx = (tid % 32) * V, ly = (tid / 32) * R;
+  int Lc = 0;
+  for (int it = 0; it < my_items; ++it) {
+    int oz0, nz, oy0, ox0;
+    item_geom(it, oz0, nz, oy0, ox0);
+    const int zs0 = oz0 + P.sz - 1;  // source plane of load Lc
+    acquire(Lc, zs0, oy0, ox0);
+    acquire(Lc + 1, zs0 + 1, oy0, ox0);
+
+    if constexpr (MODE == V3_STAR7) {
+      T zm[R][V], zc[R][V];
+      {
+        const T *s0 = reinterpret_cast<const T *>(smem + (Lc % S) * C::STAGE) + (ly + 1) * C::BW + V + lx;
+        const T *s1 = reinterpret_cast<const T *>(smem + ((Lc + 1) % S) * C::STAGE) + (ly + 1) * C::BW + V + lx;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          lds_vec<T>(zm[r], s0 + r * C::BW);
+          lds_vec<T>(zc[r], s1 + r * C::BW);
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < nz; ++j) {
+        acquire(Lc + j + 2, zs0 + j + 2, oy0, ox0);
+        const T *sm = reinterpret_cast<const T *>(smem + ((Lc + j + 1) % S) * C::STAGE) + (ly + 1) * C::BW + V + lx;
+        const T *sn = reinterpret_cast<const T *>(smem + ((Lc + j + 2) % S) * C::STAGE) + (ly + 1) * C::BW + V + lx;
+        T zp[R][V], ytop[V], ybot[V], xl[R], xr[R];
+        lds_vec<T>(ytop, sm - C::BW);
+        lds_vec<T>(ybot, sm + R * C::BW);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          lds_vec<T>(zp[r], sn + r * C::BW);
+          xl[r] = sm[r * C::BW - 1];
+          xr[r] = sm[r * C::BW + V];
+        }
+        const int gz = oz0 + j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          T res[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const T up = r > 0 ? zc[r - 1][v] : ytop[v];        // y - 1
+            const T dn = r + 1 < R ? zc[r + 1][v] : ybot[v];    // y + 1
+            const T lf = v > 0 ? zc[r][v - 1] : xl[r];          // x - 1
+            const T rt = v + 1 < V ? zc[r][v + 1] : xr[r];      // x + 1
+            // kernel index order 4,10,12,13,14,16,22 (row-major over the 3x3x3 kernel); source offset of
+            // kernel index (p,q,r) is (1-p,1-q,1-r) for a convolution, (p-1,q-1,r-1) for a correlation
+            T acc = A::from_count(0);
+            acc = A::add(A::mul(REV ? zp[r][v] : zm[r][v], K.k[4]), acc);
+            acc = A::add(A::mul(REV ? dn : up, K.k[10]), acc);
+            acc = A::add(A::mul(REV ? rt : lf, K.k[12]), acc);
+            acc = A::add(A::mul(zc[r][v], K.k[13]), acc);
+            acc = A::add(A::mul(REV ? lf : rt, K.k[14]), acc);
+            acc = A::add(A::mul(REV ? up : dn, K.k[16]), acc);
+            acc = A::add(A::mul(REV ? zm[r][v] : zp[r][v], K.k[22]), acc);
+            res[v] = acc;
+          }
+          const int gy = oy0 + ly + r, gx = ox0 + lx;
+          if (gy < P.out_h && gx < P.out_w) {
+            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_w + gx;
+            if (P.vec_store && gx + V <= P.out_w) {
+              uint4 q;
+              memcpy(&q, res, 16);
+              *reinterpret_cast<uint4 *>(dst) = q;
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+                if (gx + v < P.out_w) dst[v] = res[v];
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v) { zm[r][v] = zc[r][v]; zc[r][v] = zp[r][v]; }
+        __syncthreads();  // plane Lc+j+1 (the middle one) is no longer read by anyone
+        if (tid == 0) {
+          released = (j == nz - 1) ? Lc + nz + 2 : Lc + j + 2;
+          while (issued < total_loads && issued < released + S) issue_next();
+        }
+      }
+    } else {
+      // DENSE27: full (R+2) x (V+2) windows of planes z-1, z, z+1 in registers
+      T w[3][R + 2][V + 2];
+      auto load_win = [&](T (&dst)[R + 2][V + 2], int L) {
+        const T *sp = reinterpret_cast<const T *>(smem + (L % S) * C::STAGE) + ly * C::BW + V + lx;
+#pragma unroll
+        for (int r = 0; r < R + 2; ++r) {
+          T mid[V];
+          lds_vec<T>(mid, sp + r * C::BW);
+          dst[r][0] = sp[r * C::BW - 1];
+#pragma unroll
+          for (int v = 0; v < V; ++v) dst[r][1 + v] = mid[v];
+          dst[r][V + 1] = sp[r * C::BW + V];
+        }
+      };
+      load_win(w[0], Lc);
+      load_win(w[1], Lc + 1);
+      __syncthreads();
+      if (tid == 0) {
+        released = Lc + 2;
+        while (issued < total_loads && issued < released + S) issue_next();
+      }
+#pragma unroll 1
+      for (int j = 0; j < nz; ++j) {
+        acquire(Lc + j + 2, zs0 + j + 2, oy0, ox0);
+        load_win(w[2], Lc + j + 2);
+        const int gz = oz0 + j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          T res[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            T acc = A::from_count(0);
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+              for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                  const int dz = REV ? 1 - p : p - 1, dy = REV ? 1 - q : q - 1, dx = REV ? 1 - t : t - 1;
+                  acc = A::add(A::mul(w[1 + dz][r + 1 + dy][v + 1 + dx], K.k[p * 9 + q * 3 + t]), acc);
+                }
+            res[v] = acc;
+          }
+          const int gy = oy0 + ly + r, gx = ox0 + lx;
+          if (gy < P.out_h && gx < P.out_w) {
+            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_w + gx;
+            if (P.vec_store && gx + V <= P.out_w) {
+              uint4 q;
+              memcpy(&q, res, 16);
+              *reinterpret_cast<uint4 *>(dst) = q;
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+                if (gx + v < P.out_w) dst[v] = res[v];
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R + 2; ++r)
+#pragma unroll
+          for (int v = 0; v < V + 2; ++v) { w[0][r][v] = w[1][r][v]; w[1][r][v] = w[2][r][v]; }
+        __syncthreads();  // the newest plane now lives in registers: its stage is free
+        if (tid == 0) {
+          released = Lc + j + 3;
+          while (issued < total_loads && issued < released + S) issue_next();
+        }
+      }
+    }
+    Lc += nz + 2;
+  }
+}
+
+template <typename T, int MODE, bool REV>
+static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  using C = V3Cfg<T, MODE>;
+  const Plan &p = dp.p;
+  V3Params P;
+  std::memset(&P, 0, sizeof(P));
+  P.in_d = (int)p.in_dims[0]; P.in_h = (int)p.in_dims[1]; P.in_w = (int)p.in_dims[2];
+  P.out_d = (int)p.out_dims[0]; P.out_h = (int)p.out_dims[1]; P.out_w = (int)p.out_dims[2];
+  P.sz = (int)p.shift[0]; P.sy = (int)p.shift[1]; P.sx = (int)p.shift[2];
+  P.z0 = range ? (int)range->o0 : 0;
+  P.z1 = range ? (int)range->o1 : P.out_d;
+  if (P.z1 <= P.z0) return MB_OK;
+  P.tiles_x = (P.out_w + C::TX - 1) / C::TX;
+  P.tiles_y = (P.out_h + C::TY - 1) / C::TY;
+  P.border = p.border;
+  std::memcpy(&P.fill_bits, p.fill, 8);
+  bool fill_zero = p.border == MB_FILL;
+  for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) fill_zero = false;
+  P.zero_fill_ok = fill_zero;
+  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.out_w * sizeof(T)) % 16 == 0;
+  Coef27<T> K;
+  std::memcpy(K.k, p.c1.data(), sizeof(T) * 27);
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
+  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
+  auto kern = vol3d_kernel<T, MODE, REV>;
+  static int occ_dev[64] = {0};
+  int &occ = occ_dev[c->device & 63];
+  if (occ == 0) {
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  // z-chunks: enough work items (~8 per resident CTA) to balance the persistent CTAs, each chunk long
+  // enough that its two extra halo planes are noise
+  const int resident = c->num_sms * occ;
+  const int tiles = P.tiles_x * P.tiles_y;
+  const int nzt = P.z1 - P.z0;
+  int chunks = (8 * resident + tiles - 1) / tiles;
+  if (chunks > nzt / 32) chunks = nzt / 32;
+  if (chunks < 1) chunks = 1;
+  P.zc = (nzt + chunks - 1) / chunks;
+  chunks = (nzt + P.zc - 1) / P.zc;
+  P.nitems = tiles * chunks;
+  int grid = resident < P.nitems ? resident : P.nitems;
+  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out);
+  c->launches++;
+  c->last_kernel = MODE == V3_STAR7 ? "vol3d_star7" : "vol3d_dense27";
+  return check_cuda(c, cudaGetLastError(), "vol3d_kernel launch");
+}
+
+template <typename T>
+static bool is_star(const Plan &p) {
+  const T *k = reinterpret_cast<const T *>(p.c1.data());
+  for (int t = 0; t < 27; ++t) {
+    const bool star = t == 4 || t == 10 || t == 12 || t == 13 || t == 14 || t == 16 || t == 22;
+    if (!star && k[t] != T(0)) return false;
+  }
+  return true;
+}
+
+template <typename T>
+static int launch_v3_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const OuterRange *r) {
+  const Plan &p = dp.p;
+  // TMA wants every box row to start on a 16-byte boundary: the box begins one vector left of the
+  // tile, which is aligned exactly when the window centre of output column 0 is (mapStencil: 0)
+  if (p.shift[2] % (16 / (int)sizeof(T)) != 0) return -1;
+  const bool rev = p.kind == MB_CONV;
+  const bool star = (p.flags & MB_FLAG_ASSUME_FINITE) && is_star<T>(p);
+  if (star) return rev ? launch_v3<T, V3_STAR7, true>(c, dp, i, o, r) : launch_v3<T, V3_STAR7, false>(c, dp, i, o, r);
+  return rev ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, r) : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, r);
+}
+
+int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  const Plan &p = dp.p;
+  if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return -1;
+  for (int i = 0; i < 3; ++i) {
+    if (p.size[i] != 3 || p.in_dims[i] < 1 || p.in_dims[i] >= (1ll << 30) || p.out_dims[i] >= (1ll << 30)) return -1;
+  }
+  if (p.out_elems < c->tile_min_elems) return -1;
+  switch (p.elem) {
+    case MB_F32: return launch_v3_t<float>(c, dp, d_in, d_out, range);
+    case MB_F64: return launch_v3_t<double>(c, dp, d_in, d_out, range);
+  }
+  return -1;
+}
+
+}  // namespace mb

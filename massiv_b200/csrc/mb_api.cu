@@ -237,6 +237,7 @@ int mb_ctx_create(int device, mb_ctx **out) {
   }
   c->stream = c->own_stream;
   if (const char *fg = std::getenv("MASSIV_B200_FORCE_GENERIC")) c->force_generic = std::atoi(fg);
+  if (const char *nt = std::getenv("MASSIV_B200_NO_TMA")) c->no_tma = std::atoi(nt);
   *out = h;
   return MB_OK;
 }
@@ -275,6 +276,8 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   std::string k = key ? key : "";
   if (k == "force_generic") g.c->force_generic = (int)value;
   else if (k == "life_bitpack") g.c->life_bitpack = (int)value;
+  else if (k == "tile_min_elems") g.c->tile_min_elems = value;
+  else if (k == "no_tma") g.c->no_tma = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }

@@ -63,6 +63,43 @@ template <> struct Arith<int32_t> : IntArith<int32_t, uint32_t> {};
 template <> struct Arith<uint64_t> : IntArith<uint64_t, uint64_t> {};
 template <> struct Arith<int64_t> : IntArith<int64_t, uint64_t> {};
 
+// Correctly rounded x / n for a small positive integer n (avgStencil's `/ fromIntegral n`,
+// Array/Stencil.hs:479-481) in three operations instead of the ~15-instruction IEEE divide:
+//     q = RN(x * y), y = RN(1/n);   r = x - n*q  (exact in one FMA);   q' = RN(q + r*y)
+// Why q' == RN(x/n) for every x (n <= 1024): |q - x/n| < 2.0001 ulp(q)*n/n so r is a multiple of
+// ulp(q) below 2^12 ulp(q) and the FMA computes it exactly; q + r*y differs from x/n by less than
+// 2^-52 ulp(q), while x/n is at least ulp(q)/(4n) away from any rounding boundary (n*(2k+1) has more
+// than 53 significant bits, so x/n is never a midpoint).  The FMAs are internal to a sequence whose
+// RESULT equals the IEEE quotient; they do not fuse any two reference operations.  r is formed as
+// -fma(n, q, -x) so that x = -0 yields -0.  Guards fall back to the IEEE divide: non-finite
+// quotients (Inf would make r NaN) and subnormal-range quotients, where an even n can hit an exact
+// tie that the correction term would break.  tests/test_gpu_parity.py::test_exact_division checks
+// it against __ddiv_rn / __fdiv_rn on 2^28 random and adversarial bit patterns per n.
+struct DivCount {
+  double n_d, y_d;
+  float n_f, y_f;
+  int fast;
+};
+__device__ __forceinline__ double div_count(double x, const DivCount &d) {
+  if (!d.fast) return __ddiv_rn(x, d.n_d);
+  const double q = __dmul_rn(x, d.y_d);
+  const double r = -__fma_rn(d.n_d, q, -x);
+  const double q2 = __fma_rn(r, d.y_d, q);
+  const double aq = fabs(q);
+  if (!(aq < __longlong_as_double(0x7ff0000000000000LL)) || (aq < 8.9e-308 && x != 0.0)) return __ddiv_rn(x, d.n_d);
+  return q2;
+}
+__device__ __forceinline__ float div_count(float x, const DivCount &d) {
+  if (!d.fast) return __fdiv_rn(x, d.n_f);
+  const float q = __fmul_rn(x, d.y_f);
+  const float r = -__fmaf_rn(d.n_f, q, -x);
+  const float q2 = __fmaf_rn(r, d.y_f, q);
+  const float aq = fabsf(q);
+  if (!(aq < __int_as_float(0x7f800000)) || (aq < 4.8e-38f && x != 0.0f)) return __fdiv_rn(x, d.n_f);
+  return q2;
+}
+template <typename T> __device__ __forceinline__ T div_count(T x, const DivCount &) { return x; }  // integers: unreachable
+
 template <typename T> struct Bounds {  // minBound / maxBound
   __device__ __forceinline__ static T lo() { return T(0); }
   __device__ __forceinline__ static T hi() { return T(0); }

@@ -442,7 +442,7 @@ class DW:
             keep.append(offs)
             d.ntaps, d.tap_offsets = offs.shape[0], offs.ctypes.data
         d.flags = st.flags
-        self._keep = keep
+        d._keep = keep  # the descriptor owns the buffers its pointers refer to
         return d
 
     def size(self, stride=None) -> Ix:
