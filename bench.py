@@ -317,11 +317,28 @@ def gpu_main(args):
     b = dev.wrap(b_t.data_ptr(), grid, npdt)
     dims = _abi.dims_array(grid)
 
-    sharded = world > 1 and name == "heat3d"
+    sharded = world > 1 and wl["iterated"] and name == "heat3d"
     if sharded:
-        raise SystemExit("sharded path not wired yet")
+        # weak scaling: every rank owns a full-size slab of a (world x taller) global grid; the slab sits
+        # between its ghost planes and the library exchanges halos with ncclSend/ncclRecv every step
+        from massiv_b200 import sharding
+        sharding.init_comm(dev, dist)
+        d = M.mapStencil(border, spec[1], a).desc()
+        lo, hi = C.c_int64(), C.c_int64()
+        dev.check(L.mb_shard_halo(C.byref(d), C.byref(lo), C.byref(hi)))
+        plane = int(np.prod(grid[1:]))
+        ga_t = torch.empty((lo.value + grid[0] + hi.value) * plane, dtype=a_t.dtype, device=tdev)
+        gb_t = torch.empty_like(ga_t)
+        ga_t[lo.value * plane:(lo.value + grid[0]) * plane].copy_(a_t.view(-1))
+        del a_t, b_t
+        torch.cuda.synchronize()
+        gdims = _abi.dims_array((grid[0] * world,) + tuple(grid[1:]))
+        res = C.c_void_p()
 
-    if name == "gauss7sep":
+        def run(k):
+            dev.check(L.mb_iterate_sharded_dev(dev.handle, C.byref(d), gdims, dims, C.c_void_p(ga_t.data_ptr()),
+                                               C.c_void_p(gb_t.data_ptr()), k, C.byref(res)))
+    elif name == "gauss7sep":
         d1 = M.mapStencil(border, spec[1], a).desc()
         d2 = M.mapStencil(border, spec[2], a).desc()
         tmp_t = torch.empty_like(a_t)

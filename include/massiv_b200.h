@@ -176,12 +176,31 @@ int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, co
  * a second stream, overlapped with the interior kernel).  The rendezvous itself (who is who, the
  * unique id broadcast) is the host's job — torch.distributed in this repo. */
 #define MB_NCCL_ID_BYTES 128
+#define MB_MAX_HALO 8
+#define MB_GHOST_FILL (-1)   /* ghost plane is the Fill element (physical border)            */
+#define MB_GHOST_REMOTE (-2) /* ghost plane is received from the adjacent rank               */
+/* What one rank owns and where its ghost planes come from (host-only arithmetic). */
+typedef struct mb_shard_plan {
+  int64_t first_plane;               /* global index of the rank's first plane: rank*N/R        */
+  int64_t local_planes;              /* (rank+1)*N/R - first_plane                              */
+  int64_t halo_lo, halo_hi;          /* ghost planes below / above: centre, size-1-centre       */
+  int32_t recv_lower_from;           /* rank my lower ghost planes come from, or -1               */
+  int32_t recv_upper_from;           /* rank my upper ghost planes come from, or -1               */
+  int32_t send_first_to;             /* rank that needs my first halo_hi planes (its upper ghost), or -1 */
+  int32_t send_last_to;              /* rank that needs my last halo_lo planes (its lower ghost), or -1  */
+  int64_t ghost_lo_src[MB_MAX_HALO]; /* per ghost plane: >= 0 own local plane to copy (Edge /   */
+  int64_t ghost_hi_src[MB_MAX_HALO]; /* Reflect / Continue / 1-rank Wrap), MB_GHOST_FILL, or MB_GHOST_REMOTE */
+} mb_shard_plan;
+int mb_shard_plan_make(const mb_stencil_desc *desc, const int64_t *global_dims, int n_ranks, int rank,
+                       mb_shard_plan *out);
 int mb_nccl_unique_id(uint8_t id[MB_NCCL_ID_BYTES]);
 int mb_shard_init(mb_ctx *ctx, int n_ranks, int rank, const uint8_t id[MB_NCCL_ID_BYTES]);
 int mb_shard_halo(const mb_stencil_desc *desc, int64_t *halo_lo, int64_t *halo_hi);
 /* local buffers dev_a/dev_b hold (halo_lo + local_dims[0] + halo_hi) planes: the rank's own
- * planes at plane offset halo_lo.  global_dims[0] is the global outer extent (for the border at
- * the two ends of the global array).  *result as in mb_iterate_dev. */
+ * planes at plane offset halo_lo (ghost contents on entry are ignored).  global_dims[0] is the
+ * global outer extent (for the border at the two ends of the global array).  *result receives
+ * the BASE of the buffer (dev_a or dev_b) that holds the last state; its own planes again start
+ * at plane offset halo_lo. */
 int mb_iterate_sharded_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *global_dims,
                            const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps,
                            void **result);

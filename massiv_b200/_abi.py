@@ -32,7 +32,7 @@ SYMBOLS = [
     "mb_elem_size", "mb_out_dims", "mb_border_index", "mb_buf_alloc", "mb_buf_free", "mb_upload",
     "mb_download", "mb_host_alloc", "mb_host_free", "mb_run", "mb_run_dev", "mb_run_sep2_dev",
     "mb_run_sep2", "mb_iterate_dev", "mb_iterate", "mb_nccl_unique_id", "mb_shard_init",
-    "mb_shard_halo", "mb_iterate_sharded_dev", "mb_timer_start", "mb_timer_stop", "mb_selftest_div",
+    "mb_shard_halo", "mb_shard_plan_make", "mb_iterate_sharded_dev", "mb_timer_start", "mb_timer_stop", "mb_selftest_div",
 ]
 
 
@@ -44,6 +44,18 @@ class StencilDesc(C.Structure):
                 ("stride", C.c_int64 * MAX_RANK), ("fill", C.c_uint8 * 8),
                 ("coeffs", C.c_void_p), ("coeffs2", C.c_void_p), ("ntaps", C.c_int64),
                 ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+MAX_HALO = 8
+GHOST_FILL, GHOST_REMOTE = -1, -2
+
+
+class ShardPlan(C.Structure):
+    """mb_shard_plan"""
+    _fields_ = [("first_plane", C.c_int64), ("local_planes", C.c_int64), ("halo_lo", C.c_int64),
+                ("halo_hi", C.c_int64), ("recv_lower_from", C.c_int32), ("recv_upper_from", C.c_int32),
+                ("send_first_to", C.c_int32), ("send_last_to", C.c_int32),
+                ("ghost_lo_src", C.c_int64 * MAX_HALO), ("ghost_hi_src", C.c_int64 * MAX_HALO)]
 
 
 class MassivB200Error(RuntimeError):
@@ -108,6 +120,7 @@ def lib() -> C.CDLL:
     L.mb_nccl_unique_id.argtypes = [u8p]
     L.mb_shard_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     L.mb_shard_halo.argtypes = [dp, i64p, i64p]
+    L.mb_shard_plan_make.argtypes = [dp, i64p, C.c_int, C.c_int, C.POINTER(ShardPlan)]
     L.mb_iterate_sharded_dev.argtypes = [vp, dp, i64p, i64p, vp, vp, C.c_int64, C.POINTER(vp)]
     L.mb_selftest_div.argtypes = [vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64)]

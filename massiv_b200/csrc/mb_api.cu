@@ -85,7 +85,7 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
 int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   if (dp.p.out_elems == 0) return MB_OK;
   if (!c->force_generic) {
-    int st = launch_life(c, dp, d_in, d_out);
+    int st = range ? -1 : launch_life(c, dp, d_in, d_out);  // the Life kernels produce whole arrays
     if (st != -1) return st;
     st = launch_tile2d(c, dp, d_in, d_out, range);
     if (st != -1) return st;
@@ -251,6 +251,8 @@ int mb_ctx_destroy(mb_ctx *h) {
   c->plans.clear();
   for (int i = 0; i < 3; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->life_bound) cudaFree(c->life_bound);
+  if (c->life_flags) cudaFree(c->life_flags);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->ev_a) cudaEventDestroy(c->ev_a);

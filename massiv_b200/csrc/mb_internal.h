@@ -86,6 +86,11 @@ struct Ctx {
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
   ShardState *shard = nullptr;
+  // Life (bit-packed, temporally blocked): boundary-row mailboxes and per-CTA progress flags
+  unsigned long long *life_bound = nullptr;
+  size_t life_bound_words = 0;
+  int *life_flags = nullptr;
+  int life_nflags = 0;
 };
 
 int fail(Ctx *c, int status, const std::string &msg);
@@ -117,6 +122,8 @@ int launch_life(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out);
 int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_steps, void **result);
 
 void shard_destroy(Ctx *c);
+int shard_plan(const mb_stencil_desc *d, const int64_t *global_dims, int n_ranks, int rank, mb_shard_plan *out,
+               std::string *err);
 
 }  // namespace mb
 

@@ -1,10 +1,359 @@
+// Slab-sharded iteration across the GPUs of one box (one process per GPU).
+//
+// The reference has no distributed story (single process); this is the analogue of its
+// `iterateUntil` loop (Array/Manifest/Internal.hs:331-397) for arrays too large or too slow for one
+// GPU.  The global array is cut along the OUTERMOST dimension (contiguous in row-major, so a halo
+// plane is one contiguous block).  Per step every rank
+//   1. computes the output planes its neighbours need (the first halo_hi and last halo_lo planes),
+//   2. hands them to rank-1 / rank+1 with ncclSend/ncclRecv on a second stream,
+//   3. computes the interior planes on the main stream while the exchange is in flight,
+//   4. joins the two streams and swaps buffers.
+// The physical border of the global array is realised in the ghost planes: Fill -> constant planes,
+// Wrap -> ring neighbours, Edge/Reflect/Continue -> copies of the rank's own planes (handleBorderIndex
+// is per-dimension, Core/Index/Internal.hs:653-658, so a resolved ghost plane is an ordinary plane).
+// NCCL is resolved with dlopen at first use so that single-GPU users never need it.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "mb_internal.h"
+
 namespace mb {
-void shard_destroy(Ctx *) {}
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi &nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // reuse an already loaded NCCL (e.g. the one torch bundles), else the system library
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.lib = h;
+#define MB_SYM(field, name) api.field = (decltype(api.field))dlsym(h, name)
+    MB_SYM(GetUniqueId, "ncclGetUniqueId");
+    MB_SYM(CommInitRank, "ncclCommInitRank");
+    MB_SYM(CommDestroy, "ncclCommDestroy");
+    MB_SYM(Send, "ncclSend");
+    MB_SYM(Recv, "ncclRecv");
+    MB_SYM(GroupStart, "ncclGroupStart");
+    MB_SYM(GroupEnd, "ncclGroupEnd");
+    MB_SYM(GetErrorString, "ncclGetErrorString");
+#undef MB_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+             api.GroupEnd;
+  });
+  return api;
 }
+
+struct ShardState {
+  ncclComm_t comm = nullptr;
+  int n = 1, rank = 0;
+};
+
+void shard_destroy(Ctx *c) {
+  if (!c->shard) return;
+  if (c->shard->comm && nccl().ok) nccl().CommDestroy(c->shard->comm);
+  delete c->shard;
+  c->shard = nullptr;
+}
+
+static int check_nccl(Ctx *c, ncclResult_t r, const char *what) {
+  if (r == ncclSuccess) return MB_OK;
+  const char *s = nccl().GetErrorString ? nccl().GetErrorString(r) : "?";
+  return fail(c, MB_ERR_NCCL, std::string(what) + ": " + s);
+}
+#define MB_NCCL(ctx, expr)                              \
+  do {                                                  \
+    int _st = check_nccl((ctx), (expr), #expr);         \
+    if (_st) return _st;                                \
+  } while (0)
+
+static inline int64_t floor_mod(int64_t a, int64_t k) {
+  int64_t m = a % k;
+  return (m != 0 && ((m < 0) != (k < 0))) ? m + k : m;
+}
+
+// Where do rank `rank`'s ghost planes come from?  Ghost plane j of the lower halo is global plane
+// first - halo_lo + j; ghost plane j of the upper halo is global plane first + local + j.
+static int ghost_sources(const mb_stencil_desc *d, const Plan &p, int64_t N, int n_ranks, int rank, mb_shard_plan *out,
+                         std::string *err) {
+  auto bad = [&](int st, const char *m) { if (err) *err = m; return st; };
+  std::memset(out, 0, sizeof(*out));
+  out->first_plane = (int64_t)rank * N / n_ranks;
+  out->local_planes = (int64_t)(rank + 1) * N / n_ranks - out->first_plane;
+  out->halo_lo = p.center[0];
+  out->halo_hi = p.geom[0] - 1 - p.center[0];
+  if (out->halo_hi < 0) out->halo_hi = 0;
+  if (out->halo_lo > MB_MAX_HALO || out->halo_hi > MB_MAX_HALO) return bad(MB_ERR_UNSUPPORTED, "halo deeper than MB_MAX_HALO planes");
+  const int64_t need = out->halo_lo > out->halo_hi ? out->halo_lo : out->halo_hi;
+  if (N < n_ranks || out->local_planes < need || out->local_planes < 1)
+    return bad(MB_ERR_UNSUPPORTED, "slab thinner than the stencil halo: use fewer ranks");
+  out->recv_lower_from = out->recv_upper_from = out->send_first_to = out->send_last_to = -1;
+  for (int side = 0; side < 2; ++side) {
+    const int64_t h = side == 0 ? out->halo_lo : out->halo_hi;
+    int64_t *src = side == 0 ? out->ghost_lo_src : out->ghost_hi_src;
+    int32_t *nbr = side == 0 ? &out->recv_lower_from : &out->recv_upper_from;
+    for (int64_t j = 0; j < h; ++j) {
+      int64_t g = side == 0 ? out->first_plane - h + j : out->first_plane + out->local_planes + j;
+      src[j] = MB_GHOST_REMOTE;
+      if (g < 0 || g >= N) {  // beyond the global array: the stencil's Border decides
+        int64_t rep; int32_t is_fill;
+        int bs = border_index(d->border, N, g, &rep, &is_fill);
+        if (bs) return bad(bs, "border resolution failed");
+        if (is_fill) { src[j] = MB_GHOST_FILL; continue; }
+        g = rep;
+      }
+      if (g >= out->first_plane && g < out->first_plane + out->local_planes) {
+        src[j] = g - out->first_plane;  // one of my own planes (physical border or 1-rank wrap)
+        continue;
+      }
+      // must be owned by the adjacent rank (ring order for Wrap)
+      const int want = side == 0 ? (rank + n_ranks - 1) % n_ranks : (rank + 1) % n_ranks;
+      const int64_t wf = (int64_t)want * N / n_ranks, wl = (int64_t)(want + 1) * N / n_ranks;
+      const int64_t expect = side == 0 ? wl - h + j : wf + j;
+      if (g != expect) return bad(MB_ERR_UNSUPPORTED, "ghost plane is not on an adjacent rank: use fewer ranks");
+      *nbr = want;
+    }
+  }
+  return MB_OK;
+}
+
+// The slab plan (host only): my ghost sources, plus whom my boundary planes must be sent to (the
+// adjacent ranks whose ghost sources point at me).
+int shard_plan(const mb_stencil_desc *d, const int64_t *global_dims, int n_ranks, int rank, mb_shard_plan *out,
+               std::string *err) {
+  auto bad = [&](int st, const char *m) { if (err) *err = m; return st; };
+  if (!d || !global_dims || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return bad(MB_ERR_INVALID_DESC, "bad shard arguments");
+  Plan p;
+  int st = plan_geometry(d, global_dims, &p, err);
+  if (st) return st;
+  if (!p.same_shape() || !p.unit_stride())
+    return bad(MB_ERR_SIZE_MISMATCH, "sharded iteration needs a size-preserving (mapStencil) stencil");
+  const int64_t N = global_dims[0];
+  if ((st = ghost_sources(d, p, N, n_ranks, rank, out, err))) return st;
+  if (n_ranks > 1) {
+    mb_shard_plan q;
+    const int lower = (rank + n_ranks - 1) % n_ranks, upper = (rank + 1) % n_ranks;
+    if ((st = ghost_sources(d, p, N, n_ranks, lower, &q, err))) return st;
+    if (q.recv_upper_from == rank) out->send_first_to = lower;
+    if ((st = ghost_sources(d, p, N, n_ranks, upper, &q, err))) return st;
+    if (q.recv_lower_from == rank) out->send_last_to = upper;
+  }
+  return MB_OK;
+}
+
+// make `buf`'s ghost planes valid: local copies / fills on `stream`, neighbour planes by NCCL on comm_stream
+struct SlabGeom {
+  size_t plane_bytes;
+  int64_t local, lo, hi;
+};
+
+static int fill_local_ghosts(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, char *buf, const DevPlan &fillplan,
+                             bool fills_too, cudaStream_t stream) {
+  (void)fillplan;
+  for (int side = 0; side < 2; ++side) {
+    const int64_t h = side == 0 ? g.lo : g.hi;
+    const int64_t *src = side == 0 ? sp.ghost_lo_src : sp.ghost_hi_src;
+    for (int64_t j = 0; j < h; ++j) {
+      char *dst = buf + (size_t)(side == 0 ? j : g.lo + g.local + j) * g.plane_bytes;
+      if (src[j] >= 0) {
+        MB_CUDA(c, cudaMemcpyAsync(dst, buf + (size_t)(g.lo + src[j]) * g.plane_bytes, g.plane_bytes,
+                                   cudaMemcpyDeviceToDevice, stream));
+      } else if (src[j] == MB_GHOST_FILL && fills_too) {
+        // constant planes never change: written once per buffer by the caller (fill_const_plane)
+      }
+    }
+  }
+  return MB_OK;
+}
+
+__global__ void fill_plane_kernel(unsigned char *dst, size_t n_elems, int esize, unsigned long long bits) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_elems; i += (size_t)gridDim.x * blockDim.x) {
+    for (int b = 0; b < esize; ++b) dst[i * esize + b] = (unsigned char)(bits >> (8 * b));
+  }
+}
+
+static int exchange(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, char *buf, cudaStream_t stream) {
+  ShardState *S = c->shard;
+  if (sp.recv_lower_from < 0 && sp.recv_upper_from < 0 && sp.send_first_to < 0 && sp.send_last_to < 0) return MB_OK;
+  NcclApi &api = nccl();
+  char *first = buf + (size_t)g.lo * g.plane_bytes;                       // my first planes -> lower rank's upper ghost
+  char *last = buf + (size_t)(g.lo + g.local - g.lo) * g.plane_bytes;     // my last halo_lo planes -> upper rank's lower ghost
+  char *ghost_lo = buf;
+  char *ghost_hi = buf + (size_t)(g.lo + g.local) * g.plane_bytes;
+  MB_NCCL(c, api.GroupStart());
+  // order matters when both neighbours are the same rank (2-rank ring): sends lower-then-upper,
+  // receives upper-then-lower, so the peer's first send lands in my upper ghost
+  if (sp.send_first_to >= 0) MB_NCCL(c, api.Send(first, (size_t)g.hi * g.plane_bytes, ncclUint8, sp.send_first_to, S->comm, stream));
+  if (sp.send_last_to >= 0) MB_NCCL(c, api.Send(last, (size_t)g.lo * g.plane_bytes, ncclUint8, sp.send_last_to, S->comm, stream));
+  if (sp.recv_upper_from >= 0) MB_NCCL(c, api.Recv(ghost_hi, (size_t)g.hi * g.plane_bytes, ncclUint8, sp.recv_upper_from, S->comm, stream));
+  if (sp.recv_lower_from >= 0) MB_NCCL(c, api.Recv(ghost_lo, (size_t)g.lo * g.plane_bytes, ncclUint8, sp.recv_lower_from, S->comm, stream));
+  MB_NCCL(c, api.GroupEnd());
+  return MB_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
 extern "C" {
-int mb_nccl_unique_id(uint8_t *) { return MB_ERR_UNSUPPORTED; }
-int mb_shard_init(mb_ctx *, int, int, const uint8_t *) { return MB_ERR_UNSUPPORTED; }
-int mb_shard_halo(const mb_stencil_desc *, int64_t *, int64_t *) { return MB_ERR_UNSUPPORTED; }
-int mb_iterate_sharded_dev(mb_ctx *, const mb_stencil_desc *, const int64_t *, const int64_t *, void *, void *, int64_t, void **) { return MB_ERR_UNSUPPORTED; }
+
+int mb_shard_plan_make(const mb_stencil_desc *desc, const int64_t *global_dims, int n_ranks, int rank,
+                       mb_shard_plan *out) {
+  return shard_plan(desc, global_dims, n_ranks, rank, out, nullptr);
 }
+
+int mb_shard_halo(const mb_stencil_desc *desc, int64_t *halo_lo, int64_t *halo_hi) {
+  if (!desc || !halo_lo || !halo_hi) return MB_ERR_INVALID_DESC;
+  int64_t dims[MB_MAX_RANK];
+  for (int i = 0; i < MB_MAX_RANK; ++i) dims[i] = 1 << 20;
+  mb_shard_plan sp;
+  int st = shard_plan(desc, dims, 1, 0, &sp, nullptr);
+  if (st) return st;
+  *halo_lo = sp.halo_lo;
+  *halo_hi = sp.halo_hi;
+  return MB_OK;
+}
+
+int mb_nccl_unique_id(uint8_t *id) {
+  if (!id) return MB_ERR_INVALID_DESC;
+  NcclApi &api = nccl();
+  if (!api.ok) return MB_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) <= MB_NCCL_ID_BYTES, "ncclUniqueId larger than MB_NCCL_ID_BYTES");
+  ncclUniqueId u;
+  if (api.GetUniqueId(&u) != ncclSuccess) return MB_ERR_NCCL;
+  std::memset(id, 0, MB_NCCL_ID_BYTES);
+  std::memcpy(id, &u, sizeof(u));
+  return MB_OK;
+}
+
+int mb_shard_init(mb_ctx *h, int n_ranks, int rank, const uint8_t *id) {
+  if (!h) return MB_ERR_INVALID_DESC;
+  Ctx *c = &h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MB_CUDA(c, cudaSetDevice(c->device));
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(c, MB_ERR_INVALID_DESC, "bad rank / world size");
+  shard_destroy(c);
+  c->shard = new ShardState();
+  c->shard->n = n_ranks;
+  c->shard->rank = rank;
+  if (n_ranks == 1) return MB_OK;  // nothing to talk to: ghosts are local copies
+  if (!id) return fail(c, MB_ERR_INVALID_DESC, "missing NCCL unique id");
+  NcclApi &api = nccl();
+  if (!api.ok) return fail(c, MB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  MB_NCCL(c, api.CommInitRank(&c->shard->comm, n_ranks, u, rank));
+  return MB_OK;
+}
+
+int mb_iterate_sharded_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *global_dims,
+                           const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps, void **result) {
+  if (!h) return MB_ERR_INVALID_DESC;
+  Ctx *c = &h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MB_CUDA(c, cudaSetDevice(c->device));
+  if (!desc || !global_dims || !local_dims || !result) return fail(c, MB_ERR_INVALID_DESC, "null argument");
+  if (!c->shard) return fail(c, MB_ERR_INVALID_DESC, "mb_shard_init has not been called");
+  if (n_steps < 1) return fail(c, MB_ERR_INVALID_DESC, "iterateUntil applies the step at least once");
+  ShardState *S = c->shard;
+  mb_shard_plan sp;
+  std::string err;
+  int st = shard_plan(desc, global_dims, S->n, S->rank, &sp, &err);
+  if (st) return fail(c, st, err);
+  if (local_dims[0] != sp.local_planes) return fail(c, MB_ERR_SIZE_MISMATCH, "local_dims[0] does not match the slab plan");
+  for (int i = 1; i < desc->rank; ++i)
+    if (local_dims[i] != global_dims[i]) return fail(c, MB_ERR_SIZE_MISMATCH, "inner dimensions are not sharded");
+
+  // the local problem: the same stencil applied with NO padding along dim 0 to the slab + ghosts
+  mb_stencil_desc ld = *desc;
+  ld.pad_lo[0] = 0;
+  ld.pad_hi[0] = 0;
+  int64_t in_dims[MB_MAX_RANK];
+  for (int i = 0; i < desc->rank; ++i) in_dims[i] = local_dims[i];
+  in_dims[0] = sp.halo_lo + sp.local_planes + sp.halo_hi;
+  std::shared_ptr<DevPlan> dp;
+  if ((st = get_dev_plan(c, &ld, in_dims, &dp))) return st;
+  if (dp->p.out_dims[0] != sp.local_planes) return fail(c, MB_ERR_SIZE_MISMATCH, "internal: slab geometry");
+
+  SlabGeom g;
+  g.plane_bytes = (size_t)dp->p.esize;
+  for (int i = 1; i < desc->rank; ++i) g.plane_bytes *= (size_t)local_dims[i];
+  g.local = sp.local_planes; g.lo = sp.halo_lo; g.hi = sp.halo_hi;
+  char *bufs[2] = {(char *)dev_a, (char *)dev_b};
+
+  // constant ghost planes (Fill at a physical border) are written once into both buffers
+  unsigned long long fill_bits = 0;
+  std::memcpy(&fill_bits, desc->fill, 8);
+  const size_t plane_elems = g.plane_bytes / dp->p.esize;
+  for (int b = 0; b < 2; ++b)
+    for (int side = 0; side < 2; ++side) {
+      const int64_t hh = side == 0 ? g.lo : g.hi;
+      const int64_t *src = side == 0 ? sp.ghost_lo_src : sp.ghost_hi_src;
+      for (int64_t j = 0; j < hh; ++j)
+        if (src[j] == MB_GHOST_FILL) {
+          unsigned char *dst = (unsigned char *)bufs[b] + (size_t)(side == 0 ? j : g.lo + g.local + j) * g.plane_bytes;
+          fill_plane_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(dst, plane_elems, dp->p.esize, fill_bits);
+          c->launches++;
+        }
+    }
+  MB_CUDA(c, cudaGetLastError());
+
+  // ghosts of the initial state
+  if ((st = fill_local_ghosts(c, sp, g, bufs[0], *dp, false, c->stream))) return st;
+  MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+  MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  if ((st = exchange(c, sp, g, bufs[0], c->comm_stream))) return st;
+  MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
+  MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+
+  int cur = 0;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    char *in = bufs[cur], *out_base = bufs[1 - cur];
+    char *out = out_base + (size_t)g.lo * g.plane_bytes;  // the rank's own planes start after the lower ghost
+    const bool last = s + 1 == n_steps;
+    // 1. boundary planes first
+    int64_t top_end = g.hi < g.local ? g.hi : g.local;                 // output planes [0, top_end)
+    int64_t bot_begin = g.local - g.lo > top_end ? g.local - g.lo : top_end;  // output planes [bot_begin, local)
+    const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0;
+    if (last || !talks) { top_end = 0; bot_begin = g.local; }  // nobody waits: one launch
+    OuterRange r1{0, top_end}, r2{bot_begin, g.local}, r3{top_end, bot_begin};
+    if (r1.o1 > r1.o0 && (st = launch_plan(c, *dp, in, out, &r1))) return st;
+    if (r2.o1 > r2.o0 && (st = launch_plan(c, *dp, in, out, &r2))) return st;
+    if (!last) {
+      // physical-border ghosts of the new state are copies of its own (boundary) planes ... those may
+      // lie in the interior for deep halos, so they are refreshed after the interior launch below
+      MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+      MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+      // 2. neighbour exchange of the new boundary planes, concurrent with
+      if ((st = exchange(c, sp, g, out_base, c->comm_stream))) return st;
+      MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
+    }
+    // 3. the interior
+    if (r3.o1 > r3.o0 && (st = launch_plan(c, *dp, in, out, &r3))) return st;
+    if (!last) {
+      if ((st = fill_local_ghosts(c, sp, g, out_base, *dp, false, c->stream))) return st;
+      // 4. join
+      MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+    }
+    cur = 1 - cur;
+  }
+  *result = bufs[cur];
+  return MB_OK;
+}
+
+}  // extern "C"

@@ -118,3 +118,77 @@ def test_exact_division(elem, n, dev):
     bad, first = C.c_uint64(), C.c_uint64()
     dev.check(dev._L.mb_selftest_div(dev.handle, _abi.ELEMS[elem], n, 1 << 28, 12345 + n, C.byref(bad), C.byref(first)))
     assert bad.value == 0, f"{bad.value} mismatching quotients, first bits {first.value:#x}"
+
+
+# ---- Life: bit-packed temporally blocked kernel ---------------------------------------------------
+
+@pytest.mark.parametrize("shape,n", [((64, 64), 40), ((48, 128), 33), ((24, 64), 17), ((96, 192), 50), ((128, 256), 3),
+                                     ((16, 64), 70), ((2048, 2048), 64)])
+@pytest.mark.parametrize("border", ["wrap", "fill"])
+def test_life_bits_matches_oracle(shape, n, border, dev):
+    rng = np.random.default_rng(shape[0] * 7 + n)
+    a = (rng.random(shape) < 0.37).astype(np.uint8)
+    a[rng.random(shape) < 0.01] = 200  # first generation must still be byte-exact
+    b = M.Wrap if border == "wrap" else M.Fill(0)
+    want = O.iterate("life", a, n, size=(3, 3), border=border, fill=0, nthreads=8)
+    got = M.iterateStencil(n, b, M.lifeStencil, dev.fromHost(a)).toHost()
+    if shape[1] % 64 == 0 and (shape[1] // 64) & (shape[1] // 64 - 1) == 0:
+        assert dev.last_kernel == "life_bits", dev.last_kernel
+    assert np.array_equal(got, want)
+    dev.set_option("life_bitpack", 0)
+    try:
+        got2 = M.iterateStencil(n if shape[0] < 1000 else 5, b, M.lifeStencil, dev.fromHost(a)).toHost()
+        assert dev.last_kernel == "life_byte"
+        if shape[0] < 1000:
+            assert np.array_equal(got2, want)
+    finally:
+        dev.set_option("life_bitpack", 1)
+
+
+@pytest.mark.parametrize("border", BORDERS)
+def test_life_byte_kernel_all_borders(border, dev):
+    rng = np.random.default_rng(3)
+    for shape in ((33, 64), (7, 12), (100, 260)):
+        a = rng.integers(0, 3, shape).astype(np.uint8)
+        want = O.apply("life", a, size=(3, 3), border=border, fill=1)
+        got = M.compute(M.mapStencil(border_obj(border, 1), M.lifeStencil, dev.fromHost(a))).toHost()
+        assert dev.last_kernel == "life_byte"
+        assert np.array_equal(got, want), (border, shape)
+
+
+# ---- rank 3 ---------------------------------------------------------------------------------------------
+
+def _heat(r=0.1, dt=np.float64):
+    k = np.zeros((3, 3, 3), dt)
+    k[1, 1, 1] = 1 - 6 * r
+    for ix in ((0, 1, 1), (2, 1, 1), (1, 0, 1), (1, 2, 1), (1, 1, 0), (1, 1, 2)):
+        k[ix] = r
+    return k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("mode", ["star7", "dense27", "dense27-random", "corr-star7", "corr-random"])
+def test_vol3d_matches_oracle(mode, dtype, dev):
+    rng = np.random.default_rng(zlib.crc32(f"{mode}{np.dtype(dtype).name}".encode()))
+    for shape in ((9, 33, 70), (40, 64, 128), (5, 20, 260), (70, 40, 64), (3, 3, 3), (34, 65, 129)):
+        a = rng.standard_normal(shape).astype(dtype)
+        k = _heat(dt=dtype) if "random" not in mode else rng.standard_normal((3, 3, 3)).astype(dtype)
+        kind = "corr" if mode.startswith("corr") else "conv"
+        flags = _abi.FLAG_ASSUME_FINITE if "star7" in mode else 0
+        for border in BORDERS:
+            fill = 0.0 if rng.random() < 0.6 else 1.5
+            kw = dict(size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border=border, fill=fill)
+            want = O.apply(kind, a, **kw)
+            got = product_apply(kind, a, flags=flags, resident=True, **kw)
+            assert dev.last_kernel == ("vol3d_star7" if "star7" in mode else "vol3d_dense27"), dev.last_kernel
+            assert bits_equal(got, want), (mode, shape, border)
+
+
+def test_vol3d_non_finite_strict(dev):
+    a = np.ones((12, 40, 70))
+    a[3, 4, 5], a[8, 30, 60], a[0, 0, 0] = np.inf, np.nan, -np.inf
+    k = _heat()
+    kw = dict(size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border="fill", fill=0.0)
+    want = O.apply("conv", a, **kw)
+    got = product_apply("conv", a, resident=True, **kw)   # strict: the 20 zero taps spread NaN to the corners
+    assert dev.last_kernel == "vol3d_dense27" and np.isnan(want[2, 3, 4]) and bits_equal(got, want)
