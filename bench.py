@@ -390,7 +390,10 @@ def gpu_main(args):
     # ---- e2e: the reference-facing host->host call on pinned host buffers -------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist if world > 1 else None, torch, tdev)
+        run = None
+        a_t = b_t = ga_t = gb_t = tmp_t = None  # release the device-resident buffers before the host->host leg
+        torch.cuda.empty_cache()
+        e2e = measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist if world > 1 else None, torch, tdev, sharded)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -423,19 +426,21 @@ def gpu_main(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, tdev):
-    """same metric through the public host->host call (mb_run / mb_iterate / mb_run_sep2) with pinned
-    HOST buffers: H2D of the input and D2H of the result are inside the timed region."""
+def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, tdev, sharded):
+    """The same metric through the reference-facing host->host call — mb_run (compute . mapStencil),
+    mb_run_sep2, mb_iterate (iterateUntil) or mb_iterate_sharded — on pinned HOST buffers: the H2D copy
+    of the input and the D2H copy of the result are inside the timed region.  An iterated workload is
+    ONE call of the configured number of generations / steps, as the reference's iterateUntil is."""
+    from massiv_b200 import _abi
     wl = WORKLOADS[name]
     L = dev._L
     border = spec[0]
-    # bound the host footprint: two pinned buffers per rank
     item = np.dtype(npdt).itemsize
     try:
-        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
     except Exception:
         avail = 32 << 30
-    budget = int(avail * 0.45 / max(world, 1))
+    budget = int(avail * 0.45 / max(world, 1))  # two pinned buffers per rank must fit in host memory
     g = list(grid)
     while int(np.prod(g)) * item * 2 > budget and g[0] > 64:
         g[0] //= 2
@@ -446,37 +451,35 @@ def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, 
     dev.check(L.mb_host_alloc(dev.handle, nbytes, C.byref(hin)))
     dev.check(L.mb_host_alloc(dev.handle, nbytes, C.byref(hout)))
     src = np.ctypeslib.as_array(C.cast(hin, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(npdt).reshape(g)
-    # fill the pinned input from the device generator (cheaper than hashing on the host)
-    t = synth_device(torch, name, g, tdev, first=rank * n)
+    t = synth_device(torch, name, g, tdev, first=rank * n)  # fill the pinned input from the device generator
     torch.cuda.synchronize()
     dev.check(L.mb_download(dev.handle, hin, C.c_void_p(t.data_ptr()), nbytes))
     del t
-    from massiv_b200 import _abi
+    torch.cuda.empty_cache()
     dims = _abi.dims_array(g)
-    host_in = M.applyStencil  # noqa: F841 (keep namespace import obvious)
-    fake = np.empty(g, npdt) if False else src
     steps = args.e2e_steps or (500 if name == "heat3d" else 1000 if name == "life" else 1)
     if name == "gauss7sep":
-        d1 = M.mapStencil(border, spec[1], fake).desc()
-        d2 = M.mapStencil(border, spec[2], fake).desc()
-        call = lambda: dev.check(L.mb_run_sep2(dev.handle, C.byref(d1), C.byref(d2), dims, hin, hout))
-        passes = 1
+        d1, d2 = M.mapStencil(border, spec[1], src).desc(), M.mapStencil(border, spec[2], src).desc()
+        call, passes, cname = (lambda k: dev.check(L.mb_run_sep2(dev.handle, C.byref(d1), C.byref(d2), dims, hin, hout))), 1, "mb_run_sep2"
+    elif sharded:
+        d = M.mapStencil(border, spec[1], src).desc()
+        gdims = _abi.dims_array((g[0] * world,) + tuple(g[1:]))
+        call, passes, cname = (lambda k: dev.check(L.mb_iterate_sharded(dev.handle, C.byref(d), gdims, dims, hin, hout, k))), steps, "mb_iterate_sharded"
     elif wl["iterated"]:
-        d = M.mapStencil(border, spec[1], fake).desc()
-        call = lambda: dev.check(L.mb_iterate(dev.handle, C.byref(d), dims, hin, hout, steps))
-        passes = steps
+        d = M.mapStencil(border, spec[1], src).desc()
+        call, passes, cname = (lambda k: dev.check(L.mb_iterate(dev.handle, C.byref(d), dims, hin, hout, k))), steps, "mb_iterate"
     else:
-        d = M.mapStencil(border, spec[1], fake).desc()
-        call = lambda: dev.check(L.mb_run(dev.handle, C.byref(d), dims, hin, hout))
-        passes = 1
-    call()  # warm-up (allocates the context's device scratch)
-    reps = 1 if wl["iterated"] else 3
+        d = M.mapStencil(border, spec[1], src).desc()
+        call, passes, cname = (lambda k: dev.check(L.mb_run(dev.handle, C.byref(d), dims, hin, hout))), 1, "mb_run"
+    for _ in range(3):
+        call(2)  # warm-up: allocates the context's device scratch, touches the pinned pages
+    reps = 1 if wl["iterated"] else 5
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
-        call()
+        call(steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if dist is not None:
@@ -487,8 +490,8 @@ def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, 
     dev.check(L.mb_host_free(dev.handle, hout))
     val = float(n) * world * passes * reps / dt / 1e9
     return {"value": val, "unit": "Gcells/s", "h2d_bytes_per_step": nbytes / passes, "d2h_bytes_per_step": nbytes / passes,
-            "grid_per_gpu": list(g), "passes_per_call": passes, "seconds_per_call": dt / reps,
-            "call": "mb_iterate" if wl["iterated"] else ("mb_run_sep2" if name == "gauss7sep" else "mb_run")}
+            "grid_per_gpu": list(g), "passes_per_call": passes, "seconds_per_call": dt / reps, "call": cname,
+            "timing": "host wall clock around the blocking C call, max over ranks"}
 
 
 def main():

@@ -205,6 +205,10 @@ int mb_iterate_sharded_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64
                            const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps,
                            void **result);
 
+/* host -> host form: host_in / host_out hold this rank's OWN planes only (local_dims) */
+int mb_iterate_sharded(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *global_dims,
+                       const int64_t *local_dims, const void *host_in, void *host_out, int64_t n_steps);
+
 /* ---- device self-test (tests only) ----------------------------------------------------------- */
 /* compares the three-operation exact quotient avgStencil uses with the IEEE divide on `count`
  * random / adversarial bit patterns of element type MB_F32 or MB_F64; *mismatches must be 0 */

@@ -15,8 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(ROOT, "build", "obj")
-LIB = os.path.join(HERE, "libmassiv_b200.so")
+# tuning variants: MB_NVCC_EXTRA="-DMB_T2_WX64=2" MB_VARIANT=wx2 builds libmassiv_b200_wx2.so beside the default
+VARIANT = os.environ.get("MB_VARIANT", "")
+OBJ = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libmassiv_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 SOURCES = ["mb_plan.cpp", "mb_api.cu", "k_generic.cu", "k_tile2d.cu", "k_vol3d.cu", "k_life.cu", "mb_shard.cu",
            "k_selftest.cu"]
@@ -25,7 +27,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # never contracts; explicit fma() calls (exact-division helper) are unaffected by the flag.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-         "-I", os.path.join(ROOT, "include")]
+         "-I", os.path.join(ROOT, "include")] + os.environ.get("MB_NVCC_EXTRA", "").split()
 
 
 def _deps():

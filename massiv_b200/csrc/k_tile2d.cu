@@ -43,9 +43,17 @@ template <typename T, int N> struct Coef {
 // the staged row.  XOFF is a template parameter so that the register window is indexed statically.
 template <typename T, int OP, bool REV, int KH, int KW, int XOFF> struct T2Cfg {
   static constexpr int V = 16 / (int)sizeof(T);
-  static constexpr int TW = 32 * V;                       // one warp spans a tile row
-  static constexpr int TX = 32, TY = 8;
-  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : 4;
+#ifndef MB_T2_WX64
+#define MB_T2_WX64 1
+#endif
+#ifndef MB_T2_R64
+#define MB_T2_R64 4
+#endif
+  // warps side by side: wider tiles mean longer contiguous DRAM bursts per box row
+  static constexpr int WX = sizeof(T) == 8 ? MB_T2_WX64 : 1;
+  static constexpr int TX = 32 * WX, TY = 8 / WX;
+  static constexpr int TW = TX * V;
+  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : (sizeof(T) == 8 ? MB_T2_R64 : 4);
   static constexpr int TH = TY * R;
   static constexpr int HALO = ((XOFF + KW - 1 + V - 1) / V) * V; // halo rounded to whole vectors
   static constexpr int NV = 1 + HALO / V;

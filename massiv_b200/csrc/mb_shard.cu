@@ -261,12 +261,49 @@ int mb_shard_init(mb_ctx *h, int n_ranks, int rank, const uint8_t *id) {
   return MB_OK;
 }
 
+static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t *global_dims,
+                                  const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps, void **result);
+
 int mb_iterate_sharded_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *global_dims,
                            const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps, void **result) {
   if (!h) return MB_ERR_INVALID_DESC;
   Ctx *c = &h->c;
   std::lock_guard<std::mutex> lk(c->mu);
   MB_CUDA(c, cudaSetDevice(c->device));
+  return iterate_sharded_locked(c, desc, global_dims, local_dims, dev_a, dev_b, n_steps, result);
+}
+
+/* host -> host: this rank's slab (own planes only) in, own planes out */
+int mb_iterate_sharded(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *global_dims, const int64_t *local_dims,
+                       const void *host_in, void *host_out, int64_t n_steps) {
+  if (!h) return MB_ERR_INVALID_DESC;
+  Ctx *c = &h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MB_CUDA(c, cudaSetDevice(c->device));
+  if (!desc || !global_dims || !local_dims) return fail(c, MB_ERR_INVALID_DESC, "null argument");
+  if (!c->shard) return fail(c, MB_ERR_INVALID_DESC, "mb_shard_init has not been called");
+  mb_shard_plan sp;
+  std::string err;
+  int st = shard_plan(desc, global_dims, c->shard->n, c->shard->rank, &sp, &err);
+  if (st) return fail(c, st, err);
+  size_t plane_bytes = (size_t)mb_elem_size(desc->elem);
+  for (int i = 1; i < desc->rank; ++i) plane_bytes *= (size_t)local_dims[i];
+  const size_t own = plane_bytes * (size_t)local_dims[0];
+  const size_t total = plane_bytes * (size_t)(sp.halo_lo + local_dims[0] + sp.halo_hi);
+  void *a = nullptr, *b = nullptr, *res = nullptr;
+  if ((st = ensure_scratch(c, 0, total ? total : 1, &a))) return st;
+  if ((st = ensure_scratch(c, 1, total ? total : 1, &b))) return st;
+  if (own) MB_CUDA(c, cudaMemcpyAsync((char *)a + sp.halo_lo * plane_bytes, host_in, own, cudaMemcpyHostToDevice, c->stream));
+  if ((st = iterate_sharded_locked(c, desc, global_dims, local_dims, a, b, n_steps, &res))) return st;
+  if (own) MB_CUDA(c, cudaMemcpyAsync(host_out, (char *)res + sp.halo_lo * plane_bytes, own, cudaMemcpyDeviceToHost, c->stream));
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+}  // extern "C"
+
+static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t *global_dims,
+                                  const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps, void **result) {
   if (!desc || !global_dims || !local_dims || !result) return fail(c, MB_ERR_INVALID_DESC, "null argument");
   if (!c->shard) return fail(c, MB_ERR_INVALID_DESC, "mb_shard_init has not been called");
   if (n_steps < 1) return fail(c, MB_ERR_INVALID_DESC, "iterateUntil applies the step at least once");
@@ -355,5 +392,3 @@ int mb_iterate_sharded_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t
   *result = bufs[cur];
   return MB_OK;
 }
-
-}  // extern "C"

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/massiv_b200.h"
 
@@ -68,9 +69,18 @@ inline bool make_tensor_map(CUtensorMap *m, int elem, int esize, int rank, const
     pitch *= (uint64_t)dims[o];
   }
   if (((uint64_t)box[rank - 1] * esize) % 16 != 0) return false;
+  // L2 promotion: experiment knob MASSIV_B200_L2PROMO = 0 (none) / 64 / 128 / 256
+  static int promo = -1;
+  if (promo < 0) {
+    const char *e = getenv("MASSIV_B200_L2PROMO");
+    promo = e ? atoi(e) : 64;
+  }
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
