@@ -42,7 +42,13 @@ template <typename T, int MODE> struct V3Cfg {
   static constexpr int BW = TX + 2 * V;  // left/right halo padded to a whole vector: rows stay 16 B aligned
   static constexpr int BH = TY + 2;
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
-  static constexpr int S = MODE == V3_STAR7 ? 5 : 6;
+#ifndef MB_V3_S
+#define MB_V3_S 5
+#endif
+#ifndef MB_V3_MINB
+#define MB_V3_MINB 2
+#endif
+  static constexpr int S = MODE == V3_STAR7 ? MB_V3_S : 6;
   static constexpr int SMEM = S * STAGE + 64;
 };
 
@@ -56,7 +62,7 @@ template <typename T> __device__ __forceinline__ void lds_vec(T *dst, const T *s
 }
 
 template <typename T, int MODE, bool REV>
-__global__ void __launch_bounds__(256, MODE == V3_STAR7 ? 2 : 1)
+__global__ void __launch_bounds__(256, MODE == V3_STAR7 ? MB_V3_MINB : 1)
 vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const Coef27<T> K,
              const T *__restrict__ in, T *__restrict__ out) {
   using C = V3Cfg<T, MODE>;
@@ -208,7 +214,11 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
             if (P.vec_store && gx + V <= P.out_w) {
               uint4 q;
               memcpy(&q, res, 16);
+#ifdef MB_V3_STCS
+              __stcs(reinterpret_cast<uint4 *>(dst), q);
+#else
               *reinterpret_cast<uint4 *>(dst) = q;
+#endif
             } else {
 #pragma unroll
               for (int v = 0; v < V; ++v)
@@ -276,7 +286,11 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
             if (P.vec_store && gx + V <= P.out_w) {
               uint4 q;
               memcpy(&q, res, 16);
+#ifdef MB_V3_STCS
+              __stcs(reinterpret_cast<uint4 *>(dst), q);
+#else
               *reinterpret_cast<uint4 *>(dst) = q;
+#endif
             } else {
 #pragma unroll
               for (int v = 0; v < V; ++v)
