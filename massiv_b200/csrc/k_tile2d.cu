@@ -364,6 +364,4 @@ int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, cons
   return -1;
 }
 
-int run_sep2_fused(Ctx *, const DevPlan &, const DevPlan &, const void *, void *) { return -1; }
-
 }  // namespace mb
