@@ -280,6 +280,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "life_bitpack") g.c->life_bitpack = (int)value;
   else if (k == "tile_min_elems") g.c->tile_min_elems = value;
   else if (k == "no_tma") g.c->no_tma = (int)value;
+  else if (k == "no_known") g.c->no_known = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }

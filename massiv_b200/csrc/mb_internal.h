@@ -78,6 +78,7 @@ struct Ctx {
   int force_generic = 0;   // mb_ctx_set_option("force_generic")
   int life_bitpack = 1;    // mb_ctx_set_option("life_bitpack")
   int no_tma = 0;          // mb_ctx_set_option("no_tma"): tiles are filled with ordinary loads
+  int no_known = 0;        // mb_ctx_set_option("no_known"): skip the compile-time-coefficient kernels
   int64_t tile_min_elems = 16384;  // below this many output cells the generic kernel is used
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks

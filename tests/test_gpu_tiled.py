@@ -85,7 +85,7 @@ def test_tile2d_non_finite_and_signed_zero(dev):
             kw["coeffs"] = k.reshape(-1).tolist()
         want = oracle_apply(kind, a, **kw)
         got = product_apply(kind, a, resident=True, **kw)
-        assert dev.last_kernel == "tile2d"
+        assert dev.last_kernel in ("tile2d", "tile2d_known")  # this array is the 4-neighbour Laplacian
         assert bits_equal(got, want), kind
     d = a.astype(np.float64)
     d[5, 5] = 5e-324
