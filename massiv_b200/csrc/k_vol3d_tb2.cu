@@ -1,0 +1,326 @@
+// Temporal blocking for the iterated 3-D 7-point stencil: TWO applications of the stencil per pass
+// over HBM (iterateUntil's step applied twice, Array/Manifest/Internal.hs:331-397), so every element
+// is read once and written once per two steps — half the traffic of k_vol3d.cu.
+//
+// A CTA streams a (TYB x TXB) column along the outermost dimension.  For each new source plane it
+//   stage 1: computes the INTERMEDIATE array (one application) on the whole column tile and parks it in
+//            shared memory (cells outside the global array are the Fill element 0, not stencil values:
+//            the border rule applies to the intermediate array exactly as it does in the reference),
+//   stage 2: computes the RESULT (second application) one plane behind, on the tile minus a one-cell
+//            rim (a vector wide in x), from the parked intermediate planes.
+// Tiles overlap by that rim (overlapped tiling): the rim's stage-1 work and source loads are done
+// twice (1.14x arithmetic, 1.28x reads per two steps) in exchange for no inter-CTA communication.
+// Per-cell arithmetic is exactly that of two separate passes — same seven multiply-adds in kernel
+// order per application — so the result is bit-identical to iterating the single-step kernel.
+// Only for `Fill 0` (TMA out-of-range zero fill is the border at both levels), star-shaped finite
+// kernels (MB_FLAG_ASSUME_FINITE); everything else iterates the single-step kernels.
+#include "mb_arith.cuh"
+#include "mb_internal.h"
+#include "mb_tma.cuh"
+
+#ifndef MB_TB2_R
+#define MB_TB2_R 4  // rows per thread (tile height 8 * R)
+#endif
+
+namespace mb {
+
+struct TB2Params {
+  int in_d, in_h, in_w;  // source buffer (for sharded slabs: own planes + 2 ghost planes each side)
+  int out_d;             // result planes
+  int sz2;               // source-frame plane of result plane 0 (0 single GPU, 2 for a slab)
+  int zoff, dglob;       // source-frame plane p is global plane p + zoff of a dglob-plane array
+  int z0, z1;            // result planes produced
+  int tiles_x, tiles_y, zc, nitems;
+  int vec_store;
+};
+
+template <typename T> struct Coef27b {
+  T k[27];
+};
+
+template <typename T, int R_> struct TB2Cfg {
+  static constexpr int V = 16 / (int)sizeof(T);
+  static constexpr int R = R_;
+  static constexpr int TXB = 32 * V, TYB = 8 * R;      // stage-1 tile
+  static constexpr int OX = TXB - 2 * V, OY = TYB - 2;  // result tile
+  static constexpr int BW = TXB + 2 * V, BH = TYB + 2;  // staged box (one-cell halo, vector-padded in x)
+  static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
+  static constexpr int S = 4;
+  static constexpr int SMEM = (S + 2) * STAGE + 64;     // S source stages + 2 intermediate planes
+};
+
+template <typename T> __device__ __forceinline__ void lds_v(T *dst, const T *src) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const uint4 q = *reinterpret_cast<const uint4 *>(src);
+  T tmp[V];
+  memcpy(tmp, &q, 16);
+#pragma unroll
+  for (int v = 0; v < V; ++v) dst[v] = tmp[v];
+}
+
+// one application on the thread's R x V cells: planes below / at / above in registers (pm, pc, pp),
+// the in-plane neighbours of the middle plane from shared memory (`mid` points at the thread's first
+// cell, row pitch BW).  Kernel index order 4,10,12,13,14,16,22; see k_vol3d.cu.
+template <typename T, bool REV, int R, int V, int BW>
+__device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T (&pc)[R][V], const T (&pp)[R][V],
+                                      const Coef27b<T> &K, T (&res)[R][V]) {
+  using A = Arith<T>;
+  T ytop[V], ybot[V], xl[R], xr[R];
+  lds_v<T>(ytop, mid - BW);
+  lds_v<T>(ybot, mid + R * BW);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    xl[r] = mid[r * BW - 1];
+    xr[r] = mid[r * BW + V];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const T up = r > 0 ? pc[r - 1][v] : ytop[v];
+      const T dn = r + 1 < R ? pc[r + 1][v] : ybot[v];
+      const T lf = v > 0 ? pc[r][v - 1] : xl[r];
+      const T rt = v + 1 < V ? pc[r][v + 1] : xr[r];
+      T acc = A::from_count(0);
+      acc = A::add(A::mul(REV ? pp[r][v] : pm[r][v], K.k[4]), acc);
+      acc = A::add(A::mul(REV ? dn : up, K.k[10]), acc);
+      acc = A::add(A::mul(REV ? rt : lf, K.k[12]), acc);
+      acc = A::add(A::mul(pc[r][v], K.k[13]), acc);
+      acc = A::add(A::mul(REV ? lf : rt, K.k[14]), acc);
+      acc = A::add(A::mul(REV ? up : dn, K.k[16]), acc);
+      acc = A::add(A::mul(REV ? pm[r][v] : pp[r][v], K.k[22]), acc);
+      res[r][v] = acc;
+    }
+}
+
+template <typename T, bool REV, int R_>
+__global__ void __launch_bounds__(256, 2)
+vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out) {
+  using C = TB2Cfg<T, R_>;
+  constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  T *ubuf[2] = {reinterpret_cast<T *>(smem + S * C::STAGE), reinterpret_cast<T *>(smem + (S + 1) * C::STAGE)};
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (S + 2) * C::STAGE);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int my_items = (P.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_geom = [&](int it, int &oz0, int &nz, int &oy0, int &ox0) {
+    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = t % P.tiles_x, rest = t / P.tiles_x;
+    const int ty = rest % P.tiles_y, zi = rest / P.tiles_y;
+    oz0 = P.z0 + zi * P.zc;
+    nz = min(P.zc, P.z1 - oz0);
+    oy0 = ty * C::OY;
+    ox0 = tx * C::OX;
+  };
+  // producer (thread 0): source planes numbered globally over this CTA's items; an item of nz result
+  // planes consumes nz + 4 source planes (two above, two below)
+  int p_it = 0, p_pl = 0, issued = 0, released = 0, total_loads = 0;
+  for (int it = 0; it < my_items; ++it) {
+    int a, nz, b, c;
+    item_geom(it, a, nz, b, c);
+    total_loads += nz + 4;
+  }
+  auto issue_next = [&]() {
+    int oz0, nz, oy0, ox0;
+    item_geom(p_it, oz0, nz, oy0, ox0);
+    const int zsrc = oz0 + P.sz2 - 2 + p_pl;
+    const int s = issued % S;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
+    tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], ox0 - 2 * V, oy0 - 2, zsrc);
+    ++issued;
+    if (++p_pl == nz + 4) { p_pl = 0; ++p_it; }
+  };
+  if (tid == 0)
+    while (issued < total_loads && issued < released + S) issue_next();
+
+  uint32_t phase = 0;
+  auto acquire = [&](int L) {
+    const int s = L % S;
+    mbar_wait(&full[s], (phase >> s) & 1u);
+    phase ^= 1u << s;
+  };
+  const int lx = (tid % 32) * V, ly = (tid / 32) * R;
+  const int coff = (ly + 1) * BW + V + lx;  // the thread's first cell inside a staged box
+  auto centres = [&](T (&dst)[R][V], int L) {
+    const T *sp = reinterpret_cast<const T *>(smem + (L % S) * C::STAGE) + coff;
+#pragma unroll
+    for (int r = 0; r < R; ++r) lds_v<T>(dst[r], sp + r * BW);
+  };
+
+  int Lc = 0;
+  for (int it = 0; it < my_items; ++it) {
+    int oz0, nz, oy0, ox0;
+    item_geom(it, oz0, nz, oy0, ox0);
+    const int yB0 = oy0 - 1, xB0 = ox0 - V;  // origin of the stage-1 tile
+    const int cs = oz0 + P.sz2;              // source-frame plane of the first result plane
+    acquire(Lc);
+    acquire(Lc + 1);
+    T zm[R][V], zc[R][V], um[R][V], uc[R][V];
+    centres(zm, Lc);
+    centres(zc, Lc + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int v = 0; v < V; ++v) um[r][v] = uc[r][v] = T(0);
+    // which of the thread's cells exist in the global array (the intermediate is Fill 0 elsewhere)
+    bool in_y[R], in_x[V];
+#pragma unroll
+    for (int r = 0; r < R; ++r) in_y[r] = yB0 + ly + r >= 0 && yB0 + ly + r < P.in_h;
+#pragma unroll
+    for (int v = 0; v < V; ++v) in_x[v] = xB0 + lx + v >= 0 && xB0 + lx + v < P.in_w;
+
+#pragma unroll 1
+    for (int k = 0; k < nz + 2; ++k) {
+      const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
+      acquire(Lc + k + 2);
+      T zp[R][V], up[R][V];
+      centres(zp, Lc + k + 2);
+      // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
+      star7<T, REV, R, V, BW>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * C::STAGE) + coff, zm, zc, zp, K, up);
+      const bool in_z = ip + P.zoff >= 0 && ip + P.zoff < P.dglob;
+      T *ub = ubuf[k & 1] + coff;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (!(in_z && in_y[r] && in_x[v])) up[r][v] = T(0);
+        uint4 q;
+        memcpy(&q, up[r], 16);
+        *reinterpret_cast<uint4 *>(ub + r * BW) = q;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) { zm[r][v] = zc[r][v]; zc[r][v] = zp[r][v]; }
+      __syncthreads();  // intermediate plane ip is complete; source plane ip (the middle one) is no longer read
+      if (tid == 0) {
+        released = (k == nz + 1) ? Lc + nz + 4 : Lc + k + 2;
+        while (issued < total_loads && issued < released + S) issue_next();
+      }
+      // ---- stage 2: second application one plane behind, intermediate planes ip-2, ip-1, ip ----
+      if (k >= 2) {
+        T res[R][V];
+        star7<T, REV, R, V, BW>(ubuf[(k - 1) & 1] + coff, um, uc, up, K, res);
+        const int gz = oz0 + k - 2;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int by = ly + r, gy = yB0 + by, gx = xB0 + lx;
+          // result cells: the tile minus its rim, inside the array
+          if (by >= 1 && by < C::TYB - 1 && lx >= V && lx < C::TXB - V && gy < P.in_h && gx < P.in_w) {
+            T *dst = out + ((size_t)gz * P.in_h + gy) * P.in_w + gx;
+            if (P.vec_store && gx + V <= P.in_w) {
+              uint4 q;
+              memcpy(&q, res[r], 16);
+              *reinterpret_cast<uint4 *>(dst) = q;
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+                if (gx + v < P.in_w) dst[v] = res[r][v];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) { um[r][v] = uc[r][v]; uc[r][v] = up[r][v]; }
+      __syncthreads();  // stage 2 has read ubuf[(k-1)&1] before the next step overwrites it
+    }
+    Lc += nz + 4;
+  }
+}
+
+template <typename T, bool REV, int R_>
+static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
+                        int64_t dglob) {
+  using C = TB2Cfg<T, R_>;
+  TB2Params P;
+  std::memset(&P, 0, sizeof(P));
+  P.in_d = (int)p.in_dims[0]; P.in_h = (int)p.in_dims[1]; P.in_w = (int)p.in_dims[2];
+  P.out_d = P.in_d - 2 * sz2;
+  P.sz2 = sz2; P.zoff = (int)zoff; P.dglob = (int)dglob;
+  P.z0 = range ? (int)range->o0 : 0;
+  P.z1 = range ? (int)range->o1 : P.out_d;
+  if (P.z1 <= P.z0) return MB_OK;
+  P.tiles_x = (P.in_w + C::OX - 1) / C::OX;
+  P.tiles_y = (P.in_h + C::OY - 1) / C::OY;
+  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.in_w * sizeof(T)) % 16 == 0;
+  Coef27b<T> K;
+  std::memcpy(K.k, p.c1.data(), sizeof(T) * 27);
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
+  if (c->no_tma || !make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) return -1;
+  auto kern = vol3d_tb2_kernel<T, REV, R_>;
+  static int occ_dev[64] = {0};
+  int &occ = occ_dev[c->device & 63];
+  if (occ == 0) {
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  const int resident = c->num_sms * occ;
+  const int tiles = P.tiles_x * P.tiles_y;
+  const int nzt = P.z1 - P.z0;
+  int chunks = (8 * resident + tiles - 1) / tiles;
+  if (chunks > nzt / 64) chunks = nzt / 64;  // four extra source planes per chunk: keep chunks long
+  if (chunks < 1) chunks = 1;
+  P.zc = (nzt + chunks - 1) / chunks;
+  chunks = (nzt + P.zc - 1) / P.zc;
+  P.nitems = tiles * chunks;
+  const int grid = resident < P.nitems ? resident : P.nitems;
+  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (T *)d_out);
+  c->launches++;
+  c->last_kernel = "vol3d_tb2";
+  return check_cuda(c, cudaGetLastError(), "vol3d_tb2_kernel launch");
+}
+
+template <typename T>
+static bool star_only(const Plan &p) {
+  const T *k = reinterpret_cast<const T *>(p.c1.data());
+  for (int t = 0; t < 27; ++t) {
+    const bool star = t == 4 || t == 10 || t == 12 || t == 13 || t == 14 || t == 16 || t == 22;
+    if (!star && k[t] != T(0)) return false;
+    if (!(k[t] - k[t] == T(0))) return false;  // finite coefficients: Fill 0 stays 0 after one application
+  }
+  return true;
+}
+
+// May two steps of this single-step plan be fused?  (the plan describes ONE application)
+bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
+  if (!c->tb2 || c->force_generic || c->no_tma) return false;
+  if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return false;
+  if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
+  if (p.border != MB_FILL) return false;
+  for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) return false;
+  for (int i = 0; i < 3; ++i)
+    if (p.size[i] != 3 || p.in_dims[i] < 1 || p.in_dims[i] >= (1ll << 30)) return false;
+  if (p.shift[1] != 0 || p.shift[2] != 0 || p.out_dims[1] != p.in_dims[1] || p.out_dims[2] != p.in_dims[2]) return false;
+  if (p.out_elems < c->tile_min_elems) return false;
+  if (p.elem == MB_F32) return star_only<float>(p);
+  if (p.elem == MB_F64) return star_only<double>(p);
+  return false;
+}
+
+// Two applications in one pass.  `p` is the single-step plan whose in_dims describe the SOURCE buffer
+// handed in here; sz2 = 0: both applications are size-preserving along dim 0 (single GPU);
+// sz2 = 2: the buffer carries two ghost planes each side and in_dims[0] - 4 result planes come out.
+int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
+                     int64_t dglob) {
+  const bool rev = p.kind == MB_CONV;
+  if (p.elem == MB_F64)
+    return rev ? launch_tb2_r<double, true, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob)
+               : launch_tb2_r<double, false, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob);
+  return rev ? launch_tb2_r<float, true, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob)
+             : launch_tb2_r<float, false, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob);
+}
+
+}  // namespace mb

@@ -129,7 +129,17 @@ static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t
     if (st != -1) return st;
   }
   void *cur = a, *nxt = b;
-  for (int64_t s = 0; s < n_steps; ++s) {
+  int64_t s = 0;
+  if (vol3d_tb2_applicable(c, dp->p) && dp->p.same_shape()) {
+    // temporal blocking: pairs of steps in one pass over HBM; an odd last step runs singly below
+    for (; s + 2 <= n_steps; s += 2) {
+      st = launch_vol3d_tb2(c, dp->p, cur, nxt, nullptr, 0, 0, dp->p.in_dims[0]);
+      if (st == -1) break;  // the array cannot be described to TMA: single steps
+      if (st) return st;
+      void *t = cur; cur = nxt; nxt = t;
+    }
+  }
+  for (; s < n_steps; ++s) {
     st = launch_plan(c, *dp, cur, nxt, nullptr);
     if (st) return st;
     void *t = cur; cur = nxt; nxt = t;
@@ -281,6 +291,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "tile_min_elems") g.c->tile_min_elems = value;
   else if (k == "no_tma") g.c->no_tma = (int)value;
   else if (k == "no_known") g.c->no_known = (int)value;
+  else if (k == "tb2") g.c->tb2 = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }

@@ -79,6 +79,7 @@ struct Ctx {
   int life_bitpack = 1;    // mb_ctx_set_option("life_bitpack")
   int no_tma = 0;          // mb_ctx_set_option("no_tma"): tiles are filled with ordinary loads
   int no_known = 0;        // mb_ctx_set_option("no_known"): skip the compile-time-coefficient kernels
+  int tb2 = 1;             // mb_ctx_set_option("tb2"): fuse pairs of steps of iterated 3-D star stencils
   int64_t tile_min_elems = 16384;  // below this many output cells the generic kernel is used
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks
@@ -121,6 +122,10 @@ int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const
 int launch_life(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out);
 // Life: many generations in one go (temporal blocking); returns -1 when not applicable
 int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_steps, void **result);
+// 3-D star stencils, two steps per pass (k_vol3d_tb2.cu)
+bool vol3d_tb2_applicable(Ctx *c, const Plan &p);
+int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
+                     int64_t dglob);
 
 void shard_destroy(Ctx *c);
 int shard_plan(const mb_stencil_desc *d, const int64_t *global_dims, int n_ranks, int rank, mb_shard_plan *out,
