@@ -183,13 +183,16 @@ int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, co
 typedef struct mb_shard_plan {
   int64_t first_plane;               /* global index of the rank's first plane: rank*N/R        */
   int64_t local_planes;              /* (rank+1)*N/R - first_plane                              */
-  int64_t halo_lo, halo_hi;          /* ghost planes below / above: centre, size-1-centre       */
+  int64_t halo_lo, halo_hi;          /* ghost planes the buffers carry below / above the slab   */
   int32_t recv_lower_from;           /* rank my lower ghost planes come from, or -1               */
   int32_t recv_upper_from;           /* rank my upper ghost planes come from, or -1               */
   int32_t send_first_to;             /* rank that needs my first halo_hi planes (its upper ghost), or -1 */
   int32_t send_last_to;              /* rank that needs my last halo_lo planes (its lower ghost), or -1  */
   int64_t ghost_lo_src[MB_MAX_HALO]; /* per ghost plane: >= 0 own local plane to copy (Edge /   */
   int64_t ghost_hi_src[MB_MAX_HALO]; /* Reflect / Continue / 1-rank Wrap), MB_GHOST_FILL, or MB_GHOST_REMOTE */
+  int64_t step_halo_lo, step_halo_hi; /* planes ONE step reads beyond the slab (centre, size-1-centre);
+                                         halo_* is twice that for stencils iterated two steps per
+                                         pass (temporal blocking) */
 } mb_shard_plan;
 int mb_shard_plan_make(const mb_stencil_desc *desc, const int64_t *global_dims, int n_ranks, int rank,
                        mb_shard_plan *out);

@@ -55,7 +55,8 @@ class ShardPlan(C.Structure):
     _fields_ = [("first_plane", C.c_int64), ("local_planes", C.c_int64), ("halo_lo", C.c_int64),
                 ("halo_hi", C.c_int64), ("recv_lower_from", C.c_int32), ("recv_upper_from", C.c_int32),
                 ("send_first_to", C.c_int32), ("send_last_to", C.c_int32),
-                ("ghost_lo_src", C.c_int64 * MAX_HALO), ("ghost_hi_src", C.c_int64 * MAX_HALO)]
+                ("ghost_lo_src", C.c_int64 * MAX_HALO), ("ghost_hi_src", C.c_int64 * MAX_HALO),
+                ("step_halo_lo", C.c_int64), ("step_halo_hi", C.c_int64)]
 
 
 class MassivB200Error(RuntimeError):

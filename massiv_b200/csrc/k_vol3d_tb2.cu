@@ -21,6 +21,12 @@
 #ifndef MB_TB2_R
 #define MB_TB2_R 4  // rows per thread (tile height 8 * R)
 #endif
+#ifndef MB_TB2_MINB
+#define MB_TB2_MINB 2
+#endif
+#ifndef MB_TB2_S
+#define MB_TB2_S 4
+#endif
 
 namespace mb {
 
@@ -45,7 +51,7 @@ template <typename T, int R_> struct TB2Cfg {
   static constexpr int OX = TXB - 2 * V, OY = TYB - 2;  // result tile
   static constexpr int BW = TXB + 2 * V, BH = TYB + 2;  // staged box (one-cell halo, vector-padded in x)
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
-  static constexpr int S = 4;
+  static constexpr int S = MB_TB2_S;
   static constexpr int SMEM = (S + 2) * STAGE + 64;     // S source stages + 2 intermediate planes
 };
 
@@ -94,7 +100,7 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
 }
 
 template <typename T, bool REV, int R_>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, MB_TB2_MINB)
 vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out) {
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
@@ -290,6 +296,22 @@ static bool star_only(const Plan &p) {
     const bool star = t == 4 || t == 10 || t == 12 || t == 13 || t == 14 || t == 16 || t == 22;
     if (!star && k[t] != T(0)) return false;
     if (!(k[t] - k[t] == T(0))) return false;  // finite coefficients: Fill 0 stays 0 after one application
+  }
+  return true;
+}
+
+// descriptor-only eligibility (decides how many ghost planes a sharded slab carries)
+bool tb2_desc_eligible(const mb_stencil_desc *d) {
+  if (!d || d->rank != 3 || (d->kind != MB_CONV && d->kind != MB_CORR) || !d->coeffs) return false;
+  if (!(d->flags & MB_FLAG_ASSUME_FINITE) || d->border != MB_FILL) return false;
+  if (d->elem != MB_F32 && d->elem != MB_F64) return false;
+  const int es = d->elem == MB_F32 ? 4 : 8;
+  for (int i = 0; i < es; ++i) if (d->fill[i] != 0) return false;
+  for (int i = 0; i < 3; ++i) if (d->size[i] != 3 || d->stride[i] != 1) return false;
+  for (int t = 0; t < 27; ++t) {
+    const bool star = t == 4 || t == 10 || t == 12 || t == 13 || t == 14 || t == 16 || t == 22;
+    const double k = d->elem == MB_F32 ? (double)((const float *)d->coeffs)[t] : ((const double *)d->coeffs)[t];
+    if ((!star && k != 0.0) || !(k - k == 0.0)) return false;
   }
   return true;
 }

@@ -237,6 +237,8 @@ int mb_ctx_create(int device, mb_ctx **out) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  // (measured: giving the halo-exchange stream a higher priority is WORSE — NCCL's send/recv kernel
+  // then occupies SM slots while it waits for the peer and the persistent interior kernel starts late)
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||

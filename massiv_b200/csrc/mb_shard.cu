@@ -13,6 +13,8 @@
 // is per-dimension, Core/Index/Internal.hs:653-658, so a resolved ghost plane is an ordinary plane).
 // NCCL is resolved with dlopen at first use so that single-GPU users never need it.
 #include <dlfcn.h>
+
+#include <cstdlib>
 #include <nccl.h>
 
 #include "mb_internal.h"
@@ -94,9 +96,14 @@ static int ghost_sources(const mb_stencil_desc *d, const Plan &p, int64_t N, int
   std::memset(out, 0, sizeof(*out));
   out->first_plane = (int64_t)rank * N / n_ranks;
   out->local_planes = (int64_t)(rank + 1) * N / n_ranks - out->first_plane;
-  out->halo_lo = p.center[0];
-  out->halo_hi = p.geom[0] - 1 - p.center[0];
-  if (out->halo_hi < 0) out->halo_hi = 0;
+  out->step_halo_lo = p.center[0];
+  out->step_halo_hi = p.geom[0] - 1 - p.center[0];
+  if (out->step_halo_hi < 0) out->step_halo_hi = 0;
+  // temporally blocked stencils advance two steps per exchange and therefore keep two steps' worth
+  // of ghost planes
+  const int64_t depth = tb2_desc_eligible(d) ? 2 : 1;
+  out->halo_lo = out->step_halo_lo * depth;
+  out->halo_hi = out->step_halo_hi * depth;
   if (out->halo_lo > MB_MAX_HALO || out->halo_hi > MB_MAX_HALO) return bad(MB_ERR_UNSUPPORTED, "halo deeper than MB_MAX_HALO planes");
   const int64_t need = out->halo_lo > out->halo_hi ? out->halo_lo : out->halo_hi;
   if (N < n_ranks || out->local_planes < need || out->local_planes < 1)
@@ -316,16 +323,25 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
   for (int i = 1; i < desc->rank; ++i)
     if (local_dims[i] != global_dims[i]) return fail(c, MB_ERR_SIZE_MISMATCH, "inner dimensions are not sharded");
 
-  // the local problem: the same stencil applied with NO padding along dim 0 to the slab + ghosts
+  // the local problem: the same stencil applied with NO padding along dim 0 to the slab + ghosts.
+  // The buffers may carry more ghost planes than one step needs (extra_lo / extra_hi, temporal
+  // blocking): a single step then reads a view that skips the outermost ones.
   mb_stencil_desc ld = *desc;
   ld.pad_lo[0] = 0;
   ld.pad_hi[0] = 0;
+  const int64_t extra_lo = sp.halo_lo - sp.step_halo_lo, extra_hi = sp.halo_hi - sp.step_halo_hi;
   int64_t in_dims[MB_MAX_RANK];
   for (int i = 0; i < desc->rank; ++i) in_dims[i] = local_dims[i];
-  in_dims[0] = sp.halo_lo + sp.local_planes + sp.halo_hi;
-  std::shared_ptr<DevPlan> dp;
+  in_dims[0] = sp.step_halo_lo + sp.local_planes + sp.step_halo_hi;
+  std::shared_ptr<DevPlan> dp, dp2;
   if ((st = get_dev_plan(c, &ld, in_dims, &dp))) return st;
   if (dp->p.out_dims[0] != sp.local_planes) return fail(c, MB_ERR_SIZE_MISMATCH, "internal: slab geometry");
+  bool use_tb2 = false;
+  if (extra_lo > 0 && extra_lo == sp.step_halo_lo && extra_hi == sp.step_halo_hi && sp.halo_lo == 2 && sp.halo_hi == 2) {
+    in_dims[0] = sp.halo_lo + sp.local_planes + sp.halo_hi;
+    if ((st = get_dev_plan(c, &ld, in_dims, &dp2))) return st;
+    use_tb2 = vol3d_tb2_applicable(c, dp2->p);
+  }
 
   SlabGeom g;
   g.plane_bytes = (size_t)dp->p.esize;
@@ -358,36 +374,44 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
   MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
   MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
 
+  const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0 ||
+                     getenv("MASSIV_B200_FORCE_SPLIT") != nullptr;  // experiment knob: peel boundary planes even when alone
   int cur = 0;
-  for (int64_t s = 0; s < n_steps; ++s) {
+  for (int64_t s = 0; s < n_steps;) {
+    const bool two = use_tb2 && n_steps - s >= 2;  // a fused pair of steps, or one step
+    const int64_t adv = two ? 2 : 1;
     char *in = bufs[cur], *out_base = bufs[1 - cur];
     char *out = out_base + (size_t)g.lo * g.plane_bytes;  // the rank's own planes start after the lower ghost
-    const bool last = s + 1 == n_steps;
-    // 1. boundary planes first
-    int64_t top_end = g.hi < g.local ? g.hi : g.local;                 // output planes [0, top_end)
-    int64_t bot_begin = g.local - g.lo > top_end ? g.local - g.lo : top_end;  // output planes [bot_begin, local)
-    const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0;
+    const bool last = s + adv == n_steps;
+    auto launch = [&](const OuterRange &r) -> int {
+      if (r.o1 <= r.o0) return MB_OK;
+      if (two) return launch_vol3d_tb2(c, dp2->p, in, out, &r, (int)g.lo, sp.first_plane - g.lo, global_dims[0]);
+      return launch_plan(c, *dp, in + (size_t)extra_lo * g.plane_bytes, out, &r);
+    };
+    // 1. the planes the neighbours are waiting for (a full ghost depth at either end) first
+    int64_t top_end = g.hi < g.local ? g.hi : g.local;                        // result planes [0, top_end)
+    int64_t bot_begin = g.local - g.lo > top_end ? g.local - g.lo : top_end;  // result planes [bot_begin, local)
     if (last || !talks) { top_end = 0; bot_begin = g.local; }  // nobody waits: one launch
-    OuterRange r1{0, top_end}, r2{bot_begin, g.local}, r3{top_end, bot_begin};
-    if (r1.o1 > r1.o0 && (st = launch_plan(c, *dp, in, out, &r1))) return st;
-    if (r2.o1 > r2.o0 && (st = launch_plan(c, *dp, in, out, &r2))) return st;
+    const OuterRange r1{0, top_end}, r2{bot_begin, g.local}, r3{top_end, bot_begin};
+    if ((st = launch(r1))) return st;
+    if ((st = launch(r2))) return st;
     if (!last) {
-      // physical-border ghosts of the new state are copies of its own (boundary) planes ... those may
-      // lie in the interior for deep halos, so they are refreshed after the interior launch below
       MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
       MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
-      // 2. neighbour exchange of the new boundary planes, concurrent with
+      // 2. neighbour exchange of the new boundary planes on the second stream, concurrent with
       if ((st = exchange(c, sp, g, out_base, c->comm_stream))) return st;
       MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
     }
     // 3. the interior
-    if (r3.o1 > r3.o0 && (st = launch_plan(c, *dp, in, out, &r3))) return st;
+    if ((st = launch(r3))) return st;
     if (!last) {
+      // physical-border ghosts that are copies of own planes (Edge / Reflect / Continue / 1-rank Wrap)
       if ((st = fill_local_ghosts(c, sp, g, out_base, *dp, false, c->stream))) return st;
       // 4. join
       MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
     }
     cur = 1 - cur;
+    s += adv;
   }
   *result = bufs[cur];
   return MB_OK;

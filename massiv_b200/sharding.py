@@ -138,7 +138,10 @@ def iterate_sharded_hostcheck(n: int, desc: _abi.StencilDesc, local: np.ndarray,
         for sl, t in recv:
             b[sl] = t.numpy()
 
+    # the buffers may carry more ghost planes than one step reads (two steps' worth for temporally
+    # blocked stencils): a single step sees the view that skips the outermost ones
+    rlo, rhi = sp.step_halo_lo, sp.step_halo_hi
     for _ in range(n):
         refresh_ghosts(buf)
-        buf[lo:lo + nl] = compute(ld, buf)
+        buf[lo:lo + nl] = compute(ld, np.ascontiguousarray(buf[lo - rlo:lo + nl + rhi]))
     return buf[lo:lo + nl].copy()

@@ -25,6 +25,10 @@ def main():
     for ix in ((0, 1, 1), (2, 1, 1), (1, 0, 1), (1, 2, 1), (1, 1, 0), (1, 1, 2)):
         k[ix] = 0.1
     cases = [("heat fill0", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k).assumeFinite(), rng.random((24 * world + 3, 40, 72)), 7),
+             ("heat fused even", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k).assumeFinite(), rng.random((40 * world + 1, 64, 128)), 6),
+             ("heat thin slabs", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k).assumeFinite(), rng.random((2 * world + 1, 40, 72)), 5),
+             ("heat f32 fused", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k.astype(np.float32)).assumeFinite(),
+              rng.random((16 * world, 48, 128)).astype(np.float32), 4),
              ("heat strict", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), rng.random((16 * world, 33, 65)), 4),
              ("heat wrap", M.Wrap, M.makeConvolutionStencilFromKernel(k).assumeFinite(), rng.random((20 * world, 32, 64)), 5),
              ("heat reflect", M.Reflect, M.makeConvolutionStencilFromKernel(rng.standard_normal((3, 3, 3))), rng.random((12 * world, 32, 64)), 3),

@@ -37,6 +37,8 @@ CASES = {
     "heat3d-edge": dict(shape=(11, 5, 6), dtype=np.float64, border=("edge",), kind="conv", size=(3, 3, 3)),
     "heat3d-reflect": dict(shape=(11, 5, 6), dtype=np.float64, border=("reflect",), kind="conv", size=(3, 3, 3)),
     "heat3d-continue": dict(shape=(11, 5, 6), dtype=np.float64, border=("continue",), kind="conv", size=(3, 3, 3)),
+    # star-shaped + finite promise + Fill 0: eligible for two steps per pass, so slabs carry TWO ghost planes
+    "heat3d-star-tb2": dict(shape=(14, 6, 8), dtype=np.float64, border=("fill", 0.0), kind="conv", size=(3, 3, 3), star=True),
     "life-wrap": dict(shape=(16, 12), dtype=np.uint8, border=("wrap",), kind="life", size=(3, 3)),
     "sum5-reflect": dict(shape=(17, 9), dtype=np.int64, border=("reflect",), kind="sum", size=(5, 2)),
     "corr4-edge": dict(shape=(19, 8), dtype=np.float64, border=("edge",), kind="corr", size=(4, 3)),
@@ -55,9 +57,13 @@ def make_case(name):
         arr = rng.random(c["shape"])
     n = int(np.prod(c["size"]))
     coeffs = rng.standard_normal(n) if c["kind"] in ("conv", "corr") else None
+    flags = 0
+    if c.get("star"):
+        coeffs = np.where(np.isin(np.arange(27), (4, 10, 12, 13, 14, 16, 22)), coeffs, 0.0)
+        flags = _abi.FLAG_ASSUME_FINITE
     b = c["border"]
     border = M.Fill(b[1]) if b[0] == "fill" else {"wrap": M.Wrap, "edge": M.Edge, "reflect": M.Reflect, "continue": M.Continue}[b[0]]
-    st = M.Stencil(c["kind"], tuple(c["size"]), None, None if coeffs is None else coeffs.reshape(c["size"]))
+    st = M.Stencil(c["kind"], tuple(c["size"]), None, None if coeffs is None else coeffs.reshape(c["size"]), flags=flags)
     okw = dict(size=c["size"], border=b[0], fill=b[1] if b[0] == "fill" else 0,
                coeffs=None if coeffs is None else coeffs.tolist())
     return arr, border, st, c["kind"], okw
@@ -156,6 +162,16 @@ def test_shard_plan_partition_and_ghost_sources():
     p1 = sharding.shard_plan(d, arr.shape, 2, 1)
     assert (p.recv_upper_from, p.send_first_to, p.send_last_to, p.recv_lower_from) == (1, -1, -1, -1)
     assert (p1.recv_upper_from, p1.send_first_to, p1.send_last_to, p1.recv_lower_from) == (-1, 0, -1, -1)
+    # a star-shaped kernel with the finite promise under Fill 0 is iterated two steps per pass: the slab
+    # carries two ghost planes each side although one step reads one
+    ks = np.zeros((3, 3, 3))
+    ks[1, 1, 1], ks[0, 1, 1], ks[2, 1, 1] = 0.4, 0.1, 0.1
+    ds = M.mapStencil(M.Fill(0.0), M.makeConvolutionStencilFromKernel(ks).assumeFinite(), arr).desc()
+    ps = sharding.shard_plan(ds, arr.shape, 2, 0)
+    assert (ps.halo_lo, ps.halo_hi, ps.step_halo_lo, ps.step_halo_hi) == (2, 2, 1, 1)
+    assert list(ps.ghost_lo_src)[:2] == [_abi.GHOST_FILL] * 2 and list(ps.ghost_hi_src)[:2] == [_abi.GHOST_REMOTE] * 2
+    assert sharding.shard_plan(M.mapStencil(M.Fill(1.0), M.makeConvolutionStencilFromKernel(ks).assumeFinite(), arr).desc(),
+                               arr.shape, 2, 0).halo_lo == 1   # non-zero Fill: single steps
     # slabs thinner than the halo are refused, as is a shape-changing stencil
     with pytest.raises(M.MassivB200Error):
         sharding.shard_plan(d, arr.shape, 8, 0)
