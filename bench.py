@@ -415,7 +415,8 @@ def gpu_main(args):
             "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": name, "description": wl["text"], "grid_per_gpu": list(grid),
                        "l2": "inputs larger than L2" if cells * wl["bpc"] > 256e6 else "grid is L2-resident by definition of the workload",
-                       "kernel": kernel, "parallelism": f"slab{world}" if world > 1 else "single"},
+                       "kernel": kernel, "parallelism": f"slab{world}" if world > 1 else "single",
+                       "halo_transport": L.mb_shard_transport(dev.handle).decode() if sharded else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": kernel,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms},

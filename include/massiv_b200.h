@@ -208,6 +208,9 @@ int mb_iterate_sharded_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64
                            const int64_t *local_dims, void *dev_a, void *dev_b, int64_t n_steps,
                            void **result);
 
+/* how the last sharded call moved its halo planes: "p2p" (copy engines into IPC-mapped neighbour
+ * memory, counters in device memory — no SM involved), "nccl" (ncclSend/ncclRecv) or "none" */
+const char *mb_shard_transport(mb_ctx *ctx);
 /* host -> host form: host_in / host_out hold this rank's OWN planes only (local_dims) */
 int mb_iterate_sharded(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *global_dims,
                        const int64_t *local_dims, const void *host_in, void *host_out, int64_t n_steps);

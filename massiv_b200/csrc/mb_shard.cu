@@ -12,9 +12,11 @@
 // Wrap -> ring neighbours, Edge/Reflect/Continue -> copies of the rank's own planes (handleBorderIndex
 // is per-dimension, Core/Index/Internal.hs:653-658, so a resolved ghost plane is an ordinary plane).
 // NCCL is resolved with dlopen at first use so that single-GPU users never need it.
+#include <cuda.h>
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <map>
 #include <nccl.h>
 
 #include "mb_internal.h"
@@ -60,13 +62,62 @@ static NcclApi &nccl() {
   return api;
 }
 
+// ---- peer-memory halo exchange ---------------------------------------------------------------------
+// NCCL's send/recv kernel needs SM slots that the persistent interior kernel occupies, so the exchange
+// only ran once that kernel had drained and cost 1.8 ms per step at 4 GPUs.  The halo planes are
+// therefore moved by the copy engines over NVLink into a small staging area that every rank owns for
+// the life of its communicator and that its neighbours map with CUDA IPC (the caller's slab buffers are
+// never exported: their lifetime is the caller's business).  Two ranks hand-shake through 32-bit
+// counters in device memory, numbered by round:
+//   delivered[side]  written by the neighbour after its copy landed: "your ghosts for round r are staged"
+//   credit[side]     written by the neighbour after it copied them out: "that staging slot is free again"
+// Waiting is a stream memory operation (cuStreamWaitValue32), so no SM is involved anywhere; the
+// receiver moves staged planes into its ghost planes with a local copy (4 planes per round).
+// NCCL remains the rendezvous (IPC handles travel over it) and the fallback.
+enum { F_DELIV_LO = 0, F_DELIV_HI = 1, F_CREDIT_LO = 2, F_CREDIT_HI = 3, F_COUNT = 16 };
+static const size_t STAGE_HEADER = 256;  // the staging area starts with a magic word, plane slots follow
+
+struct IpcInfo {  // what a rank tells its neighbours at the start of an iterate call
+  cudaIpcMemHandle_t stage;
+  cudaIpcMemHandle_t flags;
+  unsigned long long stage_off, flags_off;  // of the pointer inside the exported allocation
+  unsigned long long stage_bytes;
+  int ok;
+  int pad;
+};
+
+struct PeerView {
+  char *stage = nullptr;
+  unsigned *flags = nullptr;
+};
+
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+
 struct ShardState {
   ncclComm_t comm = nullptr;
   int n = 1, rank = 0;
+  // peer-memory path
+  unsigned *flags = nullptr;        // F_COUNT counters (+ a magic word), set to `rounds` when a call starts
+  char *xstage = nullptr;           // staging area the neighbours write my ghost planes into
+  size_t xstage_bytes = 0;
+  std::vector<void *> retired;      // outgrown staging areas: freed with the communicator (a peer may still map them)
+  IpcInfo *stage = nullptr;         // device scratch for the handle exchange: [0] mine, [1] from lower, [2] from upper
+  unsigned rounds = 0;              // peer-memory rounds completed on this communicator (identical on every rank)
+  std::map<std::string, void *> opened;  // IPC handle bytes -> mapped base
+  WaitValue32Fn wait_value = nullptr;
+  GetAddressRangeFn addr_range = nullptr;
+  bool p2p_tried = false, p2p_ok = false;
+  const char *transport = "none";
 };
 
 void shard_destroy(Ctx *c) {
   if (!c->shard) return;
+  for (auto &kv : c->shard->opened) cudaIpcCloseMemHandle(kv.second);
+  if (c->shard->flags) cudaFree(c->shard->flags);
+  if (c->shard->xstage) cudaFree(c->shard->xstage);
+  for (void *p : c->shard->retired) cudaFree(p);
+  if (c->shard->stage) cudaFree(c->shard->stage);
   if (c->shard->comm && nccl().ok) nccl().CommDestroy(c->shard->comm);
   delete c->shard;
   c->shard = nullptr;
@@ -196,6 +247,8 @@ __global__ void fill_plane_kernel(unsigned char *dst, size_t n_elems, int esize,
 
 static int exchange(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, char *buf, cudaStream_t stream) {
   ShardState *S = c->shard;
+  static const bool skip = getenv("MASSIV_B200_NO_EXCHANGE") != nullptr;  // timing experiments only: results are wrong
+  if (skip) return MB_OK;
   if (sp.recv_lower_from < 0 && sp.recv_upper_from < 0 && sp.send_first_to < 0 && sp.send_last_to < 0) return MB_OK;
   NcclApi &api = nccl();
   char *first = buf + (size_t)g.lo * g.plane_bytes;                       // my first planes -> lower rank's upper ghost
@@ -213,6 +266,225 @@ static int exchange(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, char *bu
   return MB_OK;
 }
 
+// ---- peer-memory path: set-up -------------------------------------------------------------------------
+
+__global__ void set_flag_kernel(unsigned *flag, unsigned value) {
+  *reinterpret_cast<volatile unsigned *>(flag) = value;
+  __threadfence_system();
+}
+__global__ void spin_flag_kernel(const unsigned *flag, unsigned value) {  // only when stream memory ops are missing
+  while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - value) < 0) __nanosleep(200);
+  __threadfence_system();
+}
+
+struct P2P {
+  bool on = false;
+  PeerView lower, upper;  // the neighbours' staging areas / counters as mapped into this process
+};
+
+static void p2p_note(const ShardState *S, const char *what) {
+  static const bool dbg = getenv("MASSIV_B200_DEBUG_P2P") != nullptr;
+  if (dbg) fprintf(stderr, "[massiv_b200 rank %d] peer-memory halo exchange: %s\n", S->rank, what);
+}
+
+static void *open_ipc(ShardState *S, const cudaIpcMemHandle_t &h, std::vector<std::string> *used) {
+  const std::string key((const char *)&h, sizeof(h));
+  used->push_back(key);
+  auto it = S->opened.find(key);
+  if (it != S->opened.end()) return it->second;
+  void *p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  S->opened[key] = p;
+  return p;
+}
+
+static unsigned long long p2p_magic(int rank, int which) {
+  return 0x6d61737369760000ull + (unsigned long long)rank * 16 + (unsigned long long)which;
+}
+
+// where the planes bound for ghost side `side` (0 = lower, 1 = upper) of buffer parity `p` are staged
+static inline size_t stage_slot(const SlabGeom &g, int p, int side) {
+  return STAGE_HEADER + ((size_t)p * (size_t)(g.lo + g.hi) + (side ? (size_t)g.lo : 0)) * g.plane_bytes;
+}
+
+// Make sure my staging area is large enough, swap its IPC handle (and the counter block's) with the
+// neighbours over NCCL, map theirs and check the mappings.  Every rank ends up with the same answer (all
+// use peer memory, or all use NCCL): a rank that cannot export or map says so, and the verdict is relayed
+// along the chain of neighbours.
+static int setup_p2p(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, P2P *out) {
+  ShardState *S = c->shard;
+  out->on = false;
+  if (S->n < 2 || getenv("MASSIV_B200_NO_P2P")) return MB_OK;
+  NcclApi &api = nccl();
+  if (!S->p2p_tried) {
+    S->p2p_tried = true;
+    void *fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      S->wait_value = (WaitValue32Fn)fp;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      S->addr_range = (GetAddressRangeFn)fp;
+    bool ok = S->addr_range != nullptr;
+    // allocations of 2 MiB and more are blocks of their own, so their IPC handles are unambiguous
+    ok = ok && cudaMalloc(&S->flags, (size_t)2 << 20) == cudaSuccess;
+    ok = ok && cudaMemset(S->flags, 0, (size_t)2 << 20) == cudaSuccess;
+    ok = ok && cudaMalloc(&S->stage, 3 * sizeof(IpcInfo)) == cudaSuccess;
+    S->p2p_ok = ok;
+    if (!ok) p2p_note(S, "cannot allocate the counter block");
+    cudaGetLastError();
+  }
+  if (!S->stage) return MB_OK;  // cannot even say "no": the tiny allocation fails on every rank alike or not at all
+  // 1. my side: staging area, counters set to the communicator's round number, magic words
+  IpcInfo mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.ok = S->p2p_ok ? 1 : 0;
+  const size_t need = STAGE_HEADER + 2 * (size_t)(g.lo + g.hi) * g.plane_bytes;
+  if (mine.ok && S->xstage_bytes < need) {
+    if (S->xstage) S->retired.push_back(S->xstage);
+    S->xstage = nullptr;
+    S->xstage_bytes = 0;
+    const size_t bytes = need < ((size_t)2 << 20) ? ((size_t)2 << 20) : need;
+    if (cudaMalloc(&S->xstage, bytes) == cudaSuccess) S->xstage_bytes = bytes;
+    else { cudaGetLastError(); mine.ok = 0; p2p_note(S, "cannot allocate the staging area"); }
+  }
+  if (mine.ok) {
+    for (int f = 0; f < 4; ++f) set_flag_kernel<<<1, 1, 0, c->stream>>>(&S->flags[f], S->rounds);
+    const unsigned long long m0 = p2p_magic(S->rank, 0), m1 = p2p_magic(S->rank, 1);
+    MB_CUDA(c, cudaMemcpyAsync(S->xstage, &m0, 8, cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(c, cudaMemcpyAsync(S->flags + F_COUNT, &m1, 8, cudaMemcpyHostToDevice, c->stream));
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (S->addr_range(&base, &size, (CUdeviceptr)S->xstage) != CUDA_SUCCESS ||
+        cudaIpcGetMemHandle(&mine.stage, (void *)base) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    mine.stage_off = (unsigned long long)((CUdeviceptr)S->xstage - base);
+    if (mine.ok && (S->addr_range(&base, &size, (CUdeviceptr)S->flags) != CUDA_SUCCESS ||
+                    cudaIpcGetMemHandle(&mine.flags, (void *)base) != cudaSuccess)) { mine.ok = 0; cudaGetLastError(); }
+    mine.flags_off = (unsigned long long)((CUdeviceptr)S->flags - base);
+    mine.stage_bytes = S->xstage_bytes;
+    if (!mine.ok) p2p_note(S, "cannot export device memory (cudaIpcGetMemHandle)");
+  }
+  // 2. swap with the ring neighbours (ranks at a physical Fill/Edge border still have a chain neighbour)
+  const int lower = sp.recv_lower_from >= 0 ? sp.recv_lower_from : sp.send_first_to;
+  const int upper = sp.recv_upper_from >= 0 ? sp.recv_upper_from : sp.send_last_to;
+  MB_CUDA(c, cudaMemcpyAsync(&S->stage[0], &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  MB_NCCL(c, api.GroupStart());
+  if (lower >= 0) MB_NCCL(c, api.Send(&S->stage[0], sizeof(IpcInfo), ncclUint8, lower, S->comm, c->stream));
+  if (upper >= 0) MB_NCCL(c, api.Send(&S->stage[0], sizeof(IpcInfo), ncclUint8, upper, S->comm, c->stream));
+  if (upper >= 0) MB_NCCL(c, api.Recv(&S->stage[2], sizeof(IpcInfo), ncclUint8, upper, S->comm, c->stream));
+  if (lower >= 0) MB_NCCL(c, api.Recv(&S->stage[1], sizeof(IpcInfo), ncclUint8, lower, S->comm, c->stream));
+  MB_NCCL(c, api.GroupEnd());
+  IpcInfo got[2];
+  std::memset(got, 0, sizeof(got));
+  MB_CUDA(c, cudaMemcpyAsync(got, &S->stage[1], 2 * sizeof(IpcInfo), cudaMemcpyDeviceToHost, c->stream));
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  // 3. map and verify
+  int good = mine.ok;
+  PeerView lo, up;
+  std::vector<std::string> used;
+  auto map_peer = [&](const IpcInfo &info, int peer_rank, PeerView *v) {
+    if (!info.ok) { good = 0; return; }
+    if (info.stage_bytes < need) { good = 0; p2p_note(S, "a neighbour's staging area is too small"); return; }
+    char *sb = (char *)open_ipc(S, info.stage, &used);
+    char *fb = (char *)open_ipc(S, info.flags, &used);
+    if (!sb || !fb) { good = 0; p2p_note(S, "cudaIpcOpenMemHandle failed"); return; }
+    v->stage = sb + info.stage_off;
+    v->flags = (unsigned *)(fb + info.flags_off);
+    unsigned long long seen[2] = {0, 0};
+    if (cudaMemcpy(&seen[0], v->stage, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&seen[1], v->flags + F_COUNT, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaGetLastError(); good = 0; p2p_note(S, "cannot read mapped peer memory"); return;
+    }
+    if (seen[0] != p2p_magic(peer_rank, 0) || seen[1] != p2p_magic(peer_rank, 1)) { good = 0; p2p_note(S, "mapped peer memory is not the neighbour's"); }
+  };
+  if (lower >= 0) map_peer(got[0], lower, &lo);
+  if (upper >= 0) map_peer(got[1], upper, &up);
+  // mappings of staging areas the neighbours have outgrown are released (they keep the memory itself
+  // until their communicator goes away, so closing late is safe)
+  if (good) {
+    for (auto it = S->opened.begin(); it != S->opened.end();) {
+      bool keep = false;
+      for (const std::string &u : used) if (u == it->first) keep = true;
+      if (keep) { ++it; } else { cudaIpcCloseMemHandle(it->second); it = S->opened.erase(it); }
+    }
+    cudaGetLastError();
+  }
+  // 4. consensus: n_ranks-1 rounds of neighbour exchanges of one word reach every rank of a chain or ring
+  int *flagdev = reinterpret_cast<int *>(&S->stage[0]);
+  for (int hop = 0; hop < S->n - 1; ++hop) {
+    int vals[3] = {good, 1, 1};
+    MB_CUDA(c, cudaMemcpyAsync(flagdev, vals, sizeof(vals), cudaMemcpyHostToDevice, c->stream));
+    MB_NCCL(c, api.GroupStart());
+    if (lower >= 0) MB_NCCL(c, api.Send(flagdev, sizeof(int), ncclUint8, lower, S->comm, c->stream));
+    if (upper >= 0) MB_NCCL(c, api.Send(flagdev, sizeof(int), ncclUint8, upper, S->comm, c->stream));
+    if (upper >= 0) MB_NCCL(c, api.Recv(flagdev + 2, sizeof(int), ncclUint8, upper, S->comm, c->stream));
+    if (lower >= 0) MB_NCCL(c, api.Recv(flagdev + 1, sizeof(int), ncclUint8, lower, S->comm, c->stream));
+    MB_NCCL(c, api.GroupEnd());
+    MB_CUDA(c, cudaMemcpyAsync(vals, flagdev, sizeof(vals), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(c, cudaStreamSynchronize(c->stream));
+    good = good && vals[1] && vals[2];
+  }
+  if (!good) return MB_OK;
+  out->on = true;
+  out->lower = lo;
+  out->upper = up;
+  return MB_OK;
+}
+
+static int stream_wait_geq(Ctx *c, const unsigned *flag, unsigned value) {
+  ShardState *S = c->shard;
+  if (S->wait_value) {
+    if (S->wait_value((CUstream)c->stream, (CUdeviceptr)flag, value, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return MB_OK;
+    S->wait_value = nullptr;  // not supported here: fall through to the spinning kernel from now on
+  }
+  spin_flag_kernel<<<1, 1, 0, c->stream>>>(flag, value);
+  return check_cuda(c, cudaGetLastError(), "spin_flag_kernel launch");
+}
+
+// copy my boundary planes of `buf` (parity bidx) into the neighbours' staging slots and tell them.
+// The slot was last used for round - 2, so the neighbour must have copied that round out (credit_need).
+static int send_ghosts_p2p(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, const P2P &pp, char *const bufs[2], int bidx,
+                           unsigned round, unsigned credit_need) {
+  ShardState *S = c->shard;
+  char *buf = bufs[bidx];
+  if (sp.send_first_to >= 0) {  // my first halo_hi planes -> the lower neighbour's UPPER ghost planes
+    int st = stream_wait_geq(c, &S->flags[F_CREDIT_LO], credit_need);
+    if (st) return st;
+    MB_CUDA(c, cudaMemcpyAsync(pp.lower.stage + stage_slot(g, bidx, 1), buf + (size_t)g.lo * g.plane_bytes,
+                               (size_t)g.hi * g.plane_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    set_flag_kernel<<<1, 1, 0, c->stream>>>(&pp.lower.flags[F_DELIV_HI], round);
+  }
+  if (sp.send_last_to >= 0) {  // my last halo_lo planes -> the upper neighbour's LOWER ghost planes
+    int st = stream_wait_geq(c, &S->flags[F_CREDIT_HI], credit_need);
+    if (st) return st;
+    MB_CUDA(c, cudaMemcpyAsync(pp.upper.stage + stage_slot(g, bidx, 0), buf + (size_t)g.local * g.plane_bytes,
+                               (size_t)g.lo * g.plane_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    set_flag_kernel<<<1, 1, 0, c->stream>>>(&pp.upper.flags[F_DELIV_LO], round);
+  }
+  return check_cuda(c, cudaGetLastError(), "set_flag_kernel launch");
+}
+
+// wait for this round's staged planes, move them into the ghost planes of `buf` (parity bidx) and hand
+// the staging slots back to the neighbours
+static int recv_ghosts_p2p(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, const P2P &pp, char *const bufs[2], int bidx,
+                           unsigned round) {
+  ShardState *S = c->shard;
+  char *buf = bufs[bidx];
+  int st = MB_OK;
+  if (sp.recv_lower_from >= 0) {
+    if ((st = stream_wait_geq(c, &S->flags[F_DELIV_LO], round))) return st;
+    MB_CUDA(c, cudaMemcpyAsync(buf, S->xstage + stage_slot(g, bidx, 0), (size_t)g.lo * g.plane_bytes, cudaMemcpyDeviceToDevice,
+                               c->stream));
+    set_flag_kernel<<<1, 1, 0, c->stream>>>(&pp.lower.flags[F_CREDIT_HI], round);
+  }
+  if (sp.recv_upper_from >= 0) {
+    if ((st = stream_wait_geq(c, &S->flags[F_DELIV_HI], round))) return st;
+    MB_CUDA(c, cudaMemcpyAsync(buf + (size_t)(g.lo + g.local) * g.plane_bytes, S->xstage + stage_slot(g, bidx, 1),
+                               (size_t)g.hi * g.plane_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    set_flag_kernel<<<1, 1, 0, c->stream>>>(&pp.upper.flags[F_CREDIT_LO], round);
+  }
+  return check_cuda(c, cudaGetLastError(), "set_flag_kernel launch");
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -223,6 +495,8 @@ int mb_shard_plan_make(const mb_stencil_desc *desc, const int64_t *global_dims, 
                        mb_shard_plan *out) {
   return shard_plan(desc, global_dims, n_ranks, rank, out, nullptr);
 }
+
+const char *mb_shard_transport(mb_ctx *h) { return (h && h->c.shard) ? h->c.shard->transport : "none"; }
 
 int mb_shard_halo(const mb_stencil_desc *desc, int64_t *halo_lo, int64_t *halo_hi) {
   if (!desc || !halo_lo || !halo_hi) return MB_ERR_INVALID_DESC;
@@ -349,6 +623,11 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
   g.local = sp.local_planes; g.lo = sp.halo_lo; g.hi = sp.halo_hi;
   char *bufs[2] = {(char *)dev_a, (char *)dev_b};
 
+  // how the halo planes travel: peer-memory copies when every rank could map its neighbours' staging
+  // areas, NCCL send/recv otherwise (identical decision on every rank)
+  P2P pp;
+  if ((st = setup_p2p(c, sp, g, &pp))) return st;
+
   // constant ghost planes (Fill at a physical border) are written once into both buffers
   unsigned long long fill_bits = 0;
   std::memcpy(&fill_bits, desc->fill, 8);
@@ -366,13 +645,20 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
     }
   MB_CUDA(c, cudaGetLastError());
 
+  unsigned k = S->rounds;  // rounds completed on this communicator so far
+  S->transport = pp.on ? "p2p" : (S->n > 1 ? "nccl" : "none");
+
   // ghosts of the initial state
   if ((st = fill_local_ghosts(c, sp, g, bufs[0], *dp, false, c->stream))) return st;
-  MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-  MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
-  if ((st = exchange(c, sp, g, bufs[0], c->comm_stream))) return st;
-  MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
-  MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  if (pp.on) {
+    if ((st = send_ghosts_p2p(c, sp, g, pp, bufs, 0, k + 1, k))) return st;
+  } else {
+    MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+    if ((st = exchange(c, sp, g, bufs[0], c->comm_stream))) return st;
+    MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
+    MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  }
 
   const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0 ||
                      getenv("MASSIV_B200_FORCE_SPLIT") != nullptr;  // experiment knob: peel boundary planes even when alone
@@ -383,11 +669,13 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
     char *in = bufs[cur], *out_base = bufs[1 - cur];
     char *out = out_base + (size_t)g.lo * g.plane_bytes;  // the rank's own planes start after the lower ghost
     const bool last = s + adv == n_steps;
+    ++k;  // this round's number (the same on every rank)
     auto launch = [&](const OuterRange &r) -> int {
       if (r.o1 <= r.o0) return MB_OK;
       if (two) return launch_vol3d_tb2(c, dp2->p, in, out, &r, (int)g.lo, sp.first_plane - g.lo, global_dims[0]);
       return launch_plan(c, *dp, in + (size_t)extra_lo * g.plane_bytes, out, &r);
     };
+    if (pp.on && (st = recv_ghosts_p2p(c, sp, g, pp, bufs, cur, k))) return st;  // the neighbours' planes for this round
     // 1. the planes the neighbours are waiting for (a full ghost depth at either end) first
     int64_t top_end = g.hi < g.local ? g.hi : g.local;                        // result planes [0, top_end)
     int64_t bot_begin = g.local - g.lo > top_end ? g.local - g.lo : top_end;  // result planes [bot_begin, local)
@@ -396,11 +684,17 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
     if ((st = launch(r1))) return st;
     if ((st = launch(r2))) return st;
     if (!last) {
-      MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-      MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
-      // 2. neighbour exchange of the new boundary planes on the second stream, concurrent with
-      if ((st = exchange(c, sp, g, out_base, c->comm_stream))) return st;
-      MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
+      if (pp.on) {
+        // 2. copy engines push the new boundary planes into the neighbours' staging slots of that parity;
+        //    the neighbour must have copied round k-1's planes out of them
+        if ((st = send_ghosts_p2p(c, sp, g, pp, bufs, 1 - cur, k + 1, k - 1))) return st;
+      } else {
+        MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+        MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+        // 2. neighbour exchange of the new boundary planes on the second stream, concurrent with
+        if ((st = exchange(c, sp, g, out_base, c->comm_stream))) return st;
+        MB_CUDA(c, cudaEventRecord(c->ev_b, c->comm_stream));
+      }
     }
     // 3. the interior
     if ((st = launch(r3))) return st;
@@ -408,11 +702,12 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
       // physical-border ghosts that are copies of own planes (Edge / Reflect / Continue / 1-rank Wrap)
       if ((st = fill_local_ghosts(c, sp, g, out_base, *dp, false, c->stream))) return st;
       // 4. join
-      MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+      if (!pp.on) MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
     }
     cur = 1 - cur;
     s += adv;
   }
+  if (pp.on) S->rounds = k;
   *result = bufs[cur];
   return MB_OK;
 }

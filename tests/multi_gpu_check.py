@@ -45,7 +45,8 @@ def main():
         flags = torch.tensor([1 if same else 0], device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f"{name:14s} world={world} {'ok' if flags.item() else 'MISMATCH'}", flush=True)
+            how = dev._L.mb_shard_transport(dev.handle).decode()
+            print(f"{name:16s} world={world} halo via {how:4s} {'ok' if flags.item() else 'MISMATCH'}", flush=True)
         ok = ok and bool(flags.item())
     dist.barrier()
     dist.destroy_process_group()
