@@ -347,16 +347,24 @@ static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, c
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
     if (occ < 1) occ = 1;
   }
-  // z-chunks: enough work items (~8 per resident CTA) to balance the persistent CTAs, each chunk long
-  // enough that its two extra halo planes are noise
+  // z-chunks balance the persistent CTAs
   const int resident = c->num_sms * occ;
   const int tiles = P.tiles_x * P.tiles_y;
   const int nzt = P.z1 - P.z0;
-  int chunks = (8 * resident + tiles - 1) / tiles;
-  if (chunks > nzt / 32) chunks = nzt / 32;
-  if (chunks < 1) chunks = 1;
-  P.zc = (nzt + chunks - 1) / chunks;
-  chunks = (nzt + P.zc - 1) / P.zc;
+  int chunks = 1;
+  {
+    // the chunk count with the smallest estimated makespan: whole waves of resident CTAs, each item
+    // paying its halo planes and the pipeline fill
+    const int max_chunks = nzt / 16 > 1 ? (nzt / 16 < 256 ? nzt / 16 : 256) : 1;
+    long best = -1;
+    for (int cnum = 1; cnum <= max_chunks; ++cnum) {
+      const int zc = (nzt + cnum - 1) / cnum;
+      const int real = (nzt + zc - 1) / zc;
+      const long waves = ((long)tiles * real + resident - 1) / resident;
+      const long cost = waves * (zc + 2 + 3);
+      if (best < 0 || cost < best) { best = cost; chunks = real; P.zc = zc; }
+    }
+  }
   P.nitems = tiles * chunks;
   int grid = resident < P.nitems ? resident : P.nitems;
   kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out);

@@ -67,9 +67,9 @@ template <typename T> __device__ __forceinline__ void lds_v(T *dst, const T *src
 // one application on the thread's R x V cells: planes below / at / above in registers (pm, pc, pp),
 // the in-plane neighbours of the middle plane from shared memory (`mid` points at the thread's first
 // cell, row pitch BW).  Kernel index order 4,10,12,13,14,16,22; see k_vol3d.cu.
-template <typename T, bool REV, int R, int V, int BW>
+template <typename T, bool REV, int R, int V, int BW, bool SIGNAL = false>
 __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T (&pc)[R][V], const T (&pp)[R][V],
-                                      const Coef27b<T> &K, T (&res)[R][V]) {
+                                      const Coef27b<T> &K, T (&res)[R][V], uint64_t *done = nullptr) {
   using A = Arith<T>;
   T ytop[V], ybot[V], xl[R], xr[R];
   lds_v<T>(ytop, mid - BW);
@@ -78,6 +78,10 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
   for (int r = 0; r < R; ++r) {
     xl[r] = mid[r * BW - 1];
     xr[r] = mid[r * BW + V];
+  }
+  if (SIGNAL) {  // this warp's reads of the plane are done: one arrival per warp
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(done);
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -105,13 +109,16 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
   extern __shared__ __align__(128) unsigned char smem[];
-  T *ubuf[2] = {reinterpret_cast<T *>(smem + S * C::STAGE), reinterpret_cast<T *>(smem + (S + 1) * C::STAGE)};
+  unsigned char *const ubase = smem + S * C::STAGE;  // two intermediate planes, STAGE bytes apart
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (S + 2) * C::STAGE);
+  uint64_t *ufree = full + S;  // "every warp has read intermediate buffer b": it may be overwritten
   const int tid = threadIdx.x;
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_init(&ufree[0], 8);
+    mbar_init(&ufree[1], 8);
     fence_mbar_init();
   }
   __syncthreads();
@@ -126,26 +133,32 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     oy0 = ty * C::OY;
     ox0 = tx * C::OX;
   };
-  // producer (thread 0): source planes numbered globally over this CTA's items; an item of nz result
-  // planes consumes nz + 4 source planes (two above, two below)
-  int p_it = 0, p_pl = 0, issued = 0, released = 0, total_loads = 0;
-  for (int it = 0; it < my_items; ++it) {
-    int a, nz, b, c;
-    item_geom(it, a, nz, b, c);
-    total_loads += nz + 4;
+  // producer (thread 0): source planes numbered over this CTA's items; an item of nz result planes
+  // consumes nz + 4 source planes (two above, two below).  The next load's coordinates are kept
+  // incrementally so that the steady state costs a handful of instructions.
+  int p_it = 0, p_left = 0, p_x = 0, p_y = 0, p_z = 0, issued = 0, total_loads = 0;
+  if (tid == 0) {
+    for (int it = 0; it < my_items; ++it) {
+      int a, nz, b, c;
+      item_geom(it, a, nz, b, c);
+      total_loads += nz + 4;
+    }
   }
-  auto issue_next = [&]() {
-    int oz0, nz, oy0, ox0;
-    item_geom(p_it, oz0, nz, oy0, ox0);
-    const int zsrc = oz0 + P.sz2 - 2 + p_pl;
-    const int s = issued % S;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
-    tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], ox0 - 2 * V, oy0 - 2, zsrc);
-    ++issued;
-    if (++p_pl == nz + 4) { p_pl = 0; ++p_it; }
+  auto issue_upto = [&](int limit) {  // limit = planes released so far + S
+    while (issued < total_loads && issued < limit) {
+      if (p_left == 0) {
+        int oz0, nz, oy0, ox0;
+        item_geom(p_it++, oz0, nz, oy0, ox0);
+        p_left = nz + 4;
+        p_x = ox0 - 2 * V; p_y = oy0 - 2; p_z = oz0 + P.sz2 - 2;
+      }
+      const int s = issued % S;
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
+      tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], p_x, p_y, p_z);
+      ++issued; ++p_z; --p_left;
+    }
   };
-  if (tid == 0)
-    while (issued < total_loads && issued < released + S) issue_next();
+  if (tid == 0) issue_upto(S);
 
   uint32_t phase = 0;
   auto acquire = [&](int L) {
@@ -162,6 +175,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   };
 
   int Lc = 0;
+  uint32_t g = 0;  // steps taken by this CTA over all its items: intermediate planes alternate buffers with it
   for (int it = 0; it < my_items; ++it) {
     int oz0, nz, oy0, ox0;
     item_geom(it, oz0, nz, oy0, ox0);
@@ -169,76 +183,91 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     const int cs = oz0 + P.sz2;              // source-frame plane of the first result plane
     acquire(Lc);
     acquire(Lc + 1);
-    T zm[R][V], zc[R][V], um[R][V], uc[R][V];
-    centres(zm, Lc);
-    centres(zc, Lc + 1);
+    // the three source planes and the three intermediate planes a step touches live in registers and
+    // rotate by NAME (the loop is unrolled three times), not by copying
+    T Z0[R][V], Z1[R][V], Z2[R][V], U0[R][V], U1[R][V], U2[R][V];
+    centres(Z0, Lc);
+    centres(Z1, Lc + 1);
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int v = 0; v < V; ++v) um[r][v] = uc[r][v] = T(0);
-    // which of the thread's cells exist in the global array (the intermediate is Fill 0 elsewhere)
-    bool in_y[R], in_x[V];
+      for (int v = 0; v < V; ++v) U0[r][v] = U1[r][v] = T(0);
+    // which of the thread's cells exist in the global array (the intermediate is Fill 0 elsewhere),
+    // and which of its rows are result cells (the tile minus its rim, inside the array)
+    uint32_t in_yx = 0, rows = 0;
+    const int gx = xB0 + lx;
 #pragma unroll
-    for (int r = 0; r < R; ++r) in_y[r] = yB0 + ly + r >= 0 && yB0 + ly + r < P.in_h;
+    for (int r = 0; r < R; ++r) {
+      const int by = ly + r, gy = yB0 + by;
+      if (gy >= 0 && gy < P.in_h) in_yx |= 1u << r;
+      if (by >= 1 && by < C::TYB - 1 && lx >= V && lx < C::TXB - V && gy < P.in_h && gx < P.in_w) rows |= 1u << r;
+    }
 #pragma unroll
-    for (int v = 0; v < V; ++v) in_x[v] = xB0 + lx + v >= 0 && xB0 + lx + v < P.in_w;
+    for (int v = 0; v < V; ++v)
+      if (gx + v >= 0 && gx + v < P.in_w) in_yx |= 0x100u << v;
+    const bool whole = P.vec_store && gx + V <= P.in_w;
+    const long long plane = (long long)P.in_h * P.in_w;
+    long long ooff = ((long long)oz0 * P.in_h + (yB0 + ly)) * P.in_w + gx;  // row 0 of result plane oz0 (used where rows says so)
 
-#pragma unroll 1
-    for (int k = 0; k < nz + 2; ++k) {
+    // one step: source planes zm (below), zc (middle) in, zp loaded; intermediate planes um, uc in, up produced
+    auto step = [&](int k, const T (&zm)[R][V], const T (&zc)[R][V], T (&zp)[R][V], const T (&um)[R][V], const T (&uc)[R][V],
+                    T (&up)[R][V]) {
       const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
       acquire(Lc + k + 2);
-      T zp[R][V], up[R][V];
       centres(zp, Lc + k + 2);
       // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
       star7<T, REV, R, V, BW>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * C::STAGE) + coff, zm, zc, zp, K, up);
       const bool in_z = ip + P.zoff >= 0 && ip + P.zoff < P.dglob;
-      T *ub = ubuf[k & 1] + coff;
+      T *ub = reinterpret_cast<T *>(ubase + (g & 1u) * C::STAGE) + coff;
+      // the buffer was last read by step g-1's second application
+      if (g > 0) mbar_wait(&ufree[g & 1u], ((g - 1) >> 1) & 1u);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (!(in_z && in_y[r] && in_x[v])) up[r][v] = T(0);
+          if (!(in_z && ((in_yx >> r) & 1u) && ((in_yx >> (8 + v)) & 1u))) up[r][v] = T(0);
         uint4 q;
         memcpy(&q, up[r], 16);
         *reinterpret_cast<uint4 *>(ub + r * BW) = q;
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int v = 0; v < V; ++v) { zm[r][v] = zc[r][v]; zc[r][v] = zp[r][v]; }
       __syncthreads();  // intermediate plane ip is complete; source plane ip (the middle one) is no longer read
-      if (tid == 0) {
-        released = (k == nz + 1) ? Lc + nz + 4 : Lc + k + 2;
-        while (issued < total_loads && issued < released + S) issue_next();
-      }
+      if (tid == 0) issue_upto(((k == nz + 1) ? Lc + nz + 4 : Lc + k + 2) + S);
       // ---- stage 2: second application one plane behind, intermediate planes ip-2, ip-1, ip ----
+      const T *umid = reinterpret_cast<const T *>(ubase + ((g + 1u) & 1u) * C::STAGE) + coff;
       if (k >= 2) {
         T res[R][V];
-        star7<T, REV, R, V, BW>(ubuf[(k - 1) & 1] + coff, um, uc, up, K, res);
-        const int gz = oz0 + k - 2;
+        star7<T, REV, R, V, BW, true>(umid, um, uc, up, K, res, &ufree[(g + 1u) & 1u]);
+        T *dst = out + ooff;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int by = ly + r, gy = yB0 + by, gx = xB0 + lx;
-          // result cells: the tile minus its rim, inside the array
-          if (by >= 1 && by < C::TYB - 1 && lx >= V && lx < C::TXB - V && gy < P.in_h && gx < P.in_w) {
-            T *dst = out + ((size_t)gz * P.in_h + gy) * P.in_w + gx;
-            if (P.vec_store && gx + V <= P.in_w) {
+          if ((rows >> r) & 1u) {
+            if (whole) {
               uint4 q;
               memcpy(&q, res[r], 16);
-              *reinterpret_cast<uint4 *>(dst) = q;
+              *reinterpret_cast<uint4 *>(dst + (size_t)r * P.in_w) = q;
             } else {
 #pragma unroll
               for (int v = 0; v < V; ++v)
-                if (gx + v < P.in_w) dst[v] = res[r][v];
+                if (gx + v < P.in_w) dst[(size_t)r * P.in_w + v] = res[r][v];
             }
           }
         }
+        ooff += plane;
+      } else {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&ufree[(g + 1u) & 1u]);
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int v = 0; v < V; ++v) { um[r][v] = uc[r][v]; uc[r][v] = up[r][v]; }
-      __syncthreads();  // stage 2 has read ubuf[(k-1)&1] before the next step overwrites it
+      ++g;
+    };
+    const int nsteps = nz + 2;
+#pragma unroll 1
+    for (int k = 0;;) {
+      step(k, Z0, Z1, Z2, U0, U1, U2);
+      if (++k >= nsteps) break;
+      step(k, Z1, Z2, Z0, U1, U2, U0);
+      if (++k >= nsteps) break;
+      step(k, Z2, Z0, Z1, U2, U0, U1);
+      if (++k >= nsteps) break;
     }
     Lc += nz + 4;
   }
@@ -276,11 +305,21 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   const int resident = c->num_sms * occ;
   const int tiles = P.tiles_x * P.tiles_y;
   const int nzt = P.z1 - P.z0;
-  int chunks = (8 * resident + tiles - 1) / tiles;
-  if (chunks > nzt / 64) chunks = nzt / 64;  // four extra source planes per chunk: keep chunks long
-  if (chunks < 1) chunks = 1;
-  P.zc = (nzt + chunks - 1) / chunks;
-  chunks = (nzt + P.zc - 1) / P.zc;
+  // Split the outer dimension into chunks so that the items fill whole waves of the resident CTAs:
+  // every chunk costs four extra source planes (plus the pipeline fill), every partial wave costs a
+  // whole item.  Pick the chunk count with the smallest estimated makespan.
+  int chunks = 1;
+  {
+    const int max_chunks = nzt / 32 > 1 ? (nzt / 32 < 256 ? nzt / 32 : 256) : 1;
+    long best = -1;
+    for (int cnum = 1; cnum <= max_chunks; ++cnum) {
+      const int zc = (nzt + cnum - 1) / cnum;
+      const int real = (nzt + zc - 1) / zc;
+      const long waves = ((long)tiles * real + resident - 1) / resident;
+      const long cost = waves * (zc + 4 + 3);
+      if (best < 0 || cost < best) { best = cost; chunks = real; P.zc = zc; }
+    }
+  }
   P.nitems = tiles * chunks;
   const int grid = resident < P.nitems ? resident : P.nitems;
   kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (T *)d_out);

@@ -250,6 +250,7 @@ int mb_ctx_create(int device, mb_ctx **out) {
   c->stream = c->own_stream;
   if (const char *fg = std::getenv("MASSIV_B200_FORCE_GENERIC")) c->force_generic = std::atoi(fg);
   if (const char *nt = std::getenv("MASSIV_B200_NO_TMA")) c->no_tma = std::atoi(nt);
+  if (const char *tb = std::getenv("MASSIV_B200_TB2")) c->tb2 = std::atoi(tb);
   *out = h;
   return MB_OK;
 }
