@@ -72,8 +72,14 @@ typedef enum mb_kind {
   MB_TAPS,     /* make(Unsafe){Convolution,Correlation}Stencil closure form lowered to an ordered
                   tap list: acc = src[ix + off_t] * k_t + acc  Array/Stencil/Convolution.hs:44-57, 89-100 */
   MB_LIFE,     /* Game-of-Life rule on Word8                   massiv-examples/GameOfLife/app/GameOfLife.hs:15-36 */
-  MB_MAG2      /* sqrt (fmap (^2) a + fmap (^2) b), a,b FromKernel stencils of one size (Sobel)
+  MB_MAG2,     /* sqrt (fmap (^2) a + fmap (^2) b), a,b FromKernel stencils of one size (Sobel)
                   Array/Stencil/Internal.hs:105-146; massiv-bench/src/Data/Massiv/Bench/Sobel.hs:39-44 */
+  /* Integral approximation rules (Array/Numeric/Integral.hs): 1-D stencils along one dimension
+   * (size is 1 elsewhere), centre 0, coeffs[0] = dx.  g_i is the i-th sample along that dimension. */
+  MB_INT_MIDPOINT,  /* size k:    dx * (((0 + g_0) + g_1) + ... + g_{k-1})              Integral.hs:54-66   */
+  MB_INT_TRAPEZOID, /* size n+1:  (dx/2) * ((g_0 + 2*g_1 + ... + 2*g_{n-1}) + g_n)       Integral.hs:75-90   */
+  MB_INT_SIMPSON    /* size n+1, n even >= 2: (dx/3) * acc, acc = ((acc + g_i) + 4*g_{i+1}) + g_{i+2}
+                       over i = 0, 2, .., n-2                                           Integral.hs:99-118  */
 } mb_kind;
 
 /* Border (Core/Index.hs:159-195) resolved by handleBorderIndex (Core/Index.hs:236-253) */
@@ -99,7 +105,8 @@ typedef struct mb_stencil_desc {
   int64_t pad_hi[MB_MAX_RANK];   /* paddingFromBottom                                          */
   int64_t stride[MB_MAX_RANK];   /* Stride (Core/Index/Stride.hs:52-61); 1 = plain compute     */
   uint8_t fill[8];               /* Fill element (native-endian, first sizeof(elem) bytes)     */
-  const void *coeffs;            /* CONV/CORR/MAG2: prod(size) elements row-major; TAPS: ntaps */
+  const void *coeffs;            /* CONV/CORR/MAG2: prod(size) elements row-major; TAPS: ntaps;
+                                    INT_*: one element, dx                                     */
   const void *coeffs2;           /* MAG2: second kernel                                        */
   int64_t ntaps;                 /* TAPS                                                       */
   const int64_t *tap_offsets;    /* TAPS: ntaps*rank source offsets in application order       */

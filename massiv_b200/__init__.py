@@ -13,4 +13,6 @@ from .stencil import (  # noqa: F401
     mapStencil, maxStencil, minStencil, noPadding, productStencil, samePadding, sqrt, sumStencil,
 )
 
+from . import integral  # noqa: F401,E402  (Data.Massiv.Array.Numeric.Integral)
+
 __version__ = "0.1.0"

@@ -20,7 +20,7 @@ NCCL_ID_BYTES = 128
 ELEMS = {"u8": 0, "i8": 1, "u16": 2, "i16": 3, "u32": 4, "i32": 5, "u64": 6, "i64": 7, "f32": 8,
          "f64": 9, "bool32": 10}
 KINDS = {"id": 0, "sum": 1, "product": 2, "avg": 3, "max": 4, "min": 5, "conv": 6, "corr": 7,
-         "taps": 8, "life": 9, "mag2": 10}
+         "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13}
 BORDERS = {"fill": 0, "wrap": 1, "edge": 2, "reflect": 3, "continue": 4}
 FLAG_MAG2_CORR = 1
 FLAG_ASSUME_FINITE = 2

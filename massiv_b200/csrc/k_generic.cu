@@ -111,6 +111,34 @@ __global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *
         res = A::store(A::sqrt(A::add(A::mul(a, a), A::mul(b, b))));
         break;
       }
+      case MB_INT_MIDPOINT: {  // Integral.hs:64-66: dx * loop 0 (< k) (+ 1) 0 (\i -> (+ g i))
+        Acc acc = A::from_count(0);
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        res = A::store(A::mul(A::load(*(const T *)P.c1), acc));
+        break;
+      }
+      case MB_INT_TRAPEZOID: {  // Integral.hs:85-89: (dx / 2) * (loop 1 (< n) .. (g 0) (+ 2 * g i) + g n)
+        const int64_t n = P.ntaps - 1;
+        Acc acc = A::load(fetch<T>(P, in, ix, taps, fillv));
+        for (int64_t t = 1; t < n; ++t)
+          acc = A::add(acc, A::mul(A::from_count(2), A::load(fetch<T>(P, in, ix, taps + t * r, fillv))));
+        acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + n * r, fillv)));
+        res = A::store(A::mul(A::div(A::load(*(const T *)P.c1), A::from_count(2)), acc));
+        break;
+      }
+      case MB_INT_SIMPSON: {  // Integral.hs:112-117: acc + prev + 4 * g (i + 1) + fx3, then dx / 3 * acc
+        const int64_t n = P.ntaps - 1;
+        Acc acc = A::from_count(0);
+        Acc prev = A::load(fetch<T>(P, in, ix, taps, fillv));
+        for (int64_t i = 0; i < n - 1; i += 2) {
+          const Acc fx3 = A::load(fetch<T>(P, in, ix, taps + (i + 2) * r, fillv));
+          const Acc mid = A::mul(A::from_count(4), A::load(fetch<T>(P, in, ix, taps + (i + 1) * r, fillv)));
+          acc = A::add(A::add(A::add(acc, prev), mid), fx3);
+          prev = fx3;
+        }
+        res = A::store(A::mul(A::div(A::load(*(const T *)P.c1), A::from_count(3)), acc));
+        break;
+      }
       default: {  // MB_LIFE (T = uint8_t): GameOfLife.hs:15-36
         unsigned n = 0;
         for (int t = 0; t < 8; ++t) n += (unsigned)fetch<T>(P, in, ix, taps + t * r, fillv);

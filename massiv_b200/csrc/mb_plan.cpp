@@ -87,6 +87,21 @@ static int validate(const mb_stencil_desc *d, std::string *err) {
       if (d->elem != MB_U8 || d->rank != 2 || d->size[0] != 3 || d->size[1] != 3)
         return bad(MB_ERR_UNSUPPORTED, "lifeStencil is a 3x3 Word8 stencil");
       break;
+    case MB_INT_MIDPOINT: case MB_INT_TRAPEZOID: case MB_INT_SIMPSON: {
+      if (!is_float(d->elem)) return bad(MB_ERR_UNSUPPORTED, "integral rules need Fractional e");
+      if (!d->coeffs) return bad(MB_ERR_INVALID_DESC, "missing dx");
+      int along = 0;
+      int64_t len = 1;
+      for (int i = 0; i < d->rank; ++i) {
+        if (d->size[i] < 1) return bad(MB_ERR_UNSUPPORTED, "empty integration stencil");
+        if (d->size[i] != 1) { ++along; len = d->size[i]; }
+      }
+      if (along > 1) return bad(MB_ERR_INVALID_DESC, "an integration stencil runs along one dimension");
+      // Simpson's rule: `odd n` is an error in the reference; n = 0 would read outside its own window
+      if (d->kind == MB_INT_SIMPSON && (len < 3 || (len - 1) % 2 != 0))
+        return bad(MB_ERR_UNSUPPORTED, "Number of sample points for Simpson's rule stencil should be even");
+      break;
+    }
     default: return bad(MB_ERR_INVALID_DESC, "unknown stencil kind");
   }
   return MB_OK;
@@ -176,6 +191,8 @@ int make_plan(const mb_stencil_desc *d, const int64_t *in_dims, Plan *p, std::st
       if (t == 0 || o < p->min_off[i]) p->min_off[i] = o;
       if (t == 0 || o > p->max_off[i]) p->max_off[i] = o;
     }
+  const bool is_rule = d->kind == MB_INT_MIDPOINT || d->kind == MB_INT_TRAPEZOID || d->kind == MB_INT_SIMPSON;
+  if (is_rule) p->c1.assign((const uint8_t *)d->coeffs, (const uint8_t *)d->coeffs + (size_t)p->esize);  // dx
   const bool has_k = d->kind == MB_CONV || d->kind == MB_CORR || d->kind == MB_TAPS || d->kind == MB_MAG2;
   if (has_k && n > 0) {
     p->c1.assign((const uint8_t *)d->coeffs, (const uint8_t *)d->coeffs + (size_t)n * p->esize);

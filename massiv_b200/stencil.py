@@ -98,8 +98,15 @@ class Stencil:
     taps: Optional[Tuple[Ix, ...]] = None      # TAPS: effective source offsets, application order
     flags: int = 0
     scalar_size: Optional[int] = None
+    along: Optional[Tuple[int, int]] = None    # (Dim, length): size 1 everywhere but along Dim (integral rules)
 
     def _resolved(self, rank: int) -> "Stencil":
+        if self.along is not None and self.size is None:
+            dim, length = self.along
+            if not 1 <= dim <= rank:   # setDim' throws IndexDimensionException
+                raise IndexError(f"IndexDimensionException: (Dim {dim}) for an index of rank {rank}")
+            size = tuple(length if i == rank - dim else 1 for i in range(rank))   # Dim 1 is the innermost
+            return Stencil(self.kind, size, None, self.coeffs, self.coeffs2, self.taps, self.flags)
         if self.size is not None:
             if len(self.size) != rank:
                 raise ValueError(f"stencil of rank {len(self.size)} applied to an array of rank {rank}")
@@ -110,7 +117,7 @@ class Stencil:
         """Device-path extension: promise finite inputs so zero coefficients may be skipped
         (bit-identical for finite data; see MB_FLAG_ASSUME_FINITE)."""
         return Stencil(self.kind, self.size, self.center, self.coeffs, self.coeffs2, self.taps,
-                       self.flags | _abi.FLAG_ASSUME_FINITE, self.scalar_size)
+                       self.flags | _abi.FLAG_ASSUME_FINITE, self.scalar_size, self.along)
 
     # Num / Floating instances (Stencil/Internal.hs:114-174) — only the Sobel-magnitude shape
     # `sqrt (fmap (^2) a + fmap (^2) b)` lowers to a device kernel (MB_MAG2).

@@ -90,6 +90,20 @@ static int validate(const mo_desc *d) {
       if (d->elem != MO_U8 || d->rank != 2 || d->size[0] != 3 || d->size[1] != 3)
         return MO_ERR_UNSUPPORTED;
       break;
+    case MO_INT_MIDPOINT: case MO_INT_TRAPEZOID: case MO_INT_SIMPSON: {
+      /* Integral.hs:62-63: Sz (setDim' (pureIndex 1) dim k) — size 1 everywhere but along `dim` */
+      if (!is_float(d->elem)) return MO_ERR_UNSUPPORTED; /* Fractional e */
+      if (!d->coeffs) return MO_ERR_INVALID_DESC;
+      int along = 0; int64_t len = 1;
+      for (int i = 0; i < d->rank; ++i) {
+        if (d->size[i] < 1) return MO_ERR_UNSUPPORTED;
+        if (d->size[i] != 1) { ++along; len = d->size[i]; }
+      }
+      if (along > 1) return MO_ERR_INVALID_DESC;
+      /* Integral.hs:106-109: odd n is an error; n = 0 would index outside the stencil's own window */
+      if (d->kind == MO_INT_SIMPSON && (len < 3 || (len - 1) % 2 != 0)) return MO_ERR_UNSUPPORTED;
+      break;
+    }
     default: return MO_ERR_INVALID_DESC;
   }
   return MO_OK;

@@ -48,8 +48,12 @@ enum { MO_ID = 0,      /* idStencil                                  Stencil.hs:
        MO_TAPS,        /* make(Unsafe){Convolution,Correlation}Stencil closure form: an ordered
                           tap list, acc = src[ix + off_t] * k_t + acc  Convolution.hs:44-57,89-100 */
        MO_LIFE,        /* Game of Life rule stencil                  GameOfLife.hs:15-36     */
-       MO_MAG2         /* sqrt (fmap (^2) a + fmap (^2) b), a and b CONV (or CORR with flag)
+       MO_MAG2,        /* sqrt (fmap (^2) a + fmap (^2) b), a and b CONV (or CORR with flag)
                           kernels of identical size                  Bench/Sobel.hs:39-44    */
+       /* Integral approximation rules: 1-D along one dimension, centre 0, coeffs[0] = dx  */
+       MO_INT_MIDPOINT,  /* midpointStencil                          Numeric/Integral.hs:54-66   */
+       MO_INT_TRAPEZOID, /* trapezoidStencil                         Numeric/Integral.hs:75-90   */
+       MO_INT_SIMPSON    /* simpsonsStencil (n even)                 Numeric/Integral.hs:99-118  */
 };
 
 enum { MO_FILL = 0, MO_WRAP, MO_EDGE, MO_REFLECT, MO_CONTINUE };
@@ -67,7 +71,7 @@ typedef struct mo_desc {
   int64_t pad_hi[MO_MAX_RANK];   /* paddingFromBottom                                    */
   int64_t stride[MO_MAX_RANK];   /* computeWithStride; 1 everywhere for compute          */
   uint8_t fill[8];               /* Fill value, native-endian element                    */
-  const void *coeffs;            /* CONV/CORR/MAG2: prod(size) elements row-major; TAPS: ntaps */
+  const void *coeffs;            /* CONV/CORR/MAG2: prod(size) elements row-major; TAPS: ntaps; INT_*: dx */
   const void *coeffs2;           /* MAG2 second kernel                                   */
   int64_t ntaps;                 /* TAPS only                                            */
   const int64_t *tap_offsets;    /* TAPS only: ntaps*rank source offsets, application order */

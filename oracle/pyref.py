@@ -13,6 +13,7 @@ Reference (paths under /root/reference/massiv/src/Data/Massiv/):
   foldlStencil    Array/Stencil.hs:298-302      sum/product/max/min/avg :368-481
   FromKernel      Array/Stencil/Convolution.hs:64-80, 107-121    closure forms :44-57, 89-100
   strideSize      Core/Index/Stride.hs:102-105
+  integral rules  Array/Numeric/Integral.hs:54-158, 226-287
 """
 from __future__ import annotations
 
@@ -201,6 +202,89 @@ def life_stencil() -> Stencil:  # GameOfLife.hs:15-36
             n = u8((int(n) + int(get((i + a, j + b)))) & 0xFF)
         return rules(get((i, j)), n)
     return Stencil((3, 3), (1, 1), func)
+
+
+# ---- integral approximation (Array/Numeric/Integral.hs) ------------------------------------------
+# Dim 1 is the innermost dimension: setDim' ix (Dim d) touches axis rank - d.
+
+def _along(rank: int, dim: int, v: int, rest: int) -> Ix:
+    if not 1 <= dim <= rank:
+        raise IndexError(dim)
+    return tuple(v if i == rank - dim else rest for i in range(rank))
+
+
+def midpoint_stencil(dx, dim: int, k: int, rank: int, dt) -> Stencil:  # Integral.hs:54-66
+    def func(get, ix):
+        acc = dt.type(0)
+        for i in range(k):  # loop 0 (< k) (+ 1) 0 (\i -> (+ g i)):  acc + g i
+            acc = dt.type(acc + get(tuple(a + b for a, b in zip(ix, _along(rank, dim, i, 0)))))
+        return dt.type(dt.type(dx) * acc)
+    return Stencil(_along(rank, dim, k, 1), (0,) * rank, func)
+
+
+def trapezoid_stencil(dx, dim: int, n: int, rank: int, dt) -> Stencil:  # Integral.hs:75-90
+    def func(get, ix):
+        g = lambda i: get(tuple(a + b for a, b in zip(ix, _along(rank, dim, i, 0))))
+        acc = g(0)
+        for i in range(1, n):  # loop 1 (< n) (+ 1) (g 0) (\i -> (+ 2 * g i))
+            acc = dt.type(acc + dt.type(dt.type(2) * g(i)))
+        acc = dt.type(acc + g(n))
+        return dt.type(dt.type(dt.type(dx) / dt.type(2)) * acc)
+    return Stencil(_along(rank, dim, n + 1, 1), (0,) * rank, func)
+
+
+def simpsons_stencil(dx, dim: int, n: int, rank: int, dt) -> Stencil:  # Integral.hs:99-118
+    if n % 2:
+        raise ValueError("Number of sample points for Simpson's rule stencil should be even")
+
+    def func(get, ix):
+        g = lambda i: get(tuple(a + b for a, b in zip(ix, _along(rank, dim, i, 0))))
+
+        def sim_acc(i, state):
+            prev, acc = state
+            fx3 = g(i + 2)
+            new = dt.type(dt.type(dt.type(acc + prev) + dt.type(dt.type(4) * g(i + 1))) + fx3)
+            return fx3, new
+        state = sim_acc(0, (g(0), dt.type(0)))
+        i = 2
+        while i < n - 1:
+            state = sim_acc(i, state)
+            i += 2
+        return dt.type(dt.type(dt.type(dx) / dt.type(3)) * state[1])
+    return Stencil(_along(rank, dim, n + 1, 1), (0,) * rank, func)
+
+
+def integrate_with(stencil_of, dim: int, n: int, arr: np.ndarray) -> np.ndarray:  # Integral.hs:121-135
+    rank = arr.ndim
+    st = stencil_of(dim, n)
+    return map_stencil(("fill", arr.dtype.type(0)), st, arr, stride=_along(rank, dim, n, 1))
+
+
+def integral_approx(stencil_of, d, sz: Ix, n: int, arr: np.ndarray) -> np.ndarray:  # Integral.hs:138-158
+    dt = arr.dtype
+    dx = dt.type(dt.type(d) / dt.type(n))
+    for dim in range(1, arr.ndim + 1):
+        arr = integrate_with(lambda dm, k: stencil_of(dx, dm, k, arr.ndim, dt), dim, n, arr)
+    return arr[tuple(slice(0, s) for s in sz)]
+
+
+def from_function(f, a, d, sz: Ix, n: int, dt) -> np.ndarray:  # Integral.hs:226-251
+    shape = tuple(n * s + 1 for s in sz)
+    scale = lambda i: dt.type(dt.type(a) + dt.type(dt.type(dt.type(d) * dt.type(i)) / dt.type(n)))
+    out = np.empty(shape, dt)
+    for ix in _row_major(shape):
+        out[ix] = f(scale, ix)
+    return out
+
+
+def from_function_midpoint(f, a, d, sz: Ix, n: int, dt) -> np.ndarray:  # Integral.hs:253-287
+    shape = tuple(n * s for s in sz)
+    dx2 = dt.type(dt.type(dt.type(d) / dt.type(n)) / dt.type(2))
+    scale = lambda i: dt.type(dt.type(dx2 + dt.type(a)) + dt.type(dt.type(dt.type(d) * dt.type(i)) / dt.type(n)))
+    out = np.empty(shape, dt)
+    for ix in _row_major(shape):
+        out[ix] = f(scale, ix)
+    return out
 
 
 def same_padding(st: Stencil):
