@@ -45,8 +45,29 @@ WORKLOADS = {
     "gauss7sep": dict(dtype="f32", grid=(32768, 32768), bpc=8, iterated=False,
                       text="7x7 Gaussian as separable 1x7 then 7x1 two-pass, Float, Edge border"),
     "life": dict(dtype="u8", grid=(2048, 2048), bpc=2, iterated=True, text="Game of Life 3x3 Word8, Wrap border"),
+    # strided evaluation.  Cells are OUTPUT cells; bytes are input + output.
+    "pool3": dict(dtype="i64", grid=(24576, 24576), stride=(3, 3), iterated=False,
+                  text="computeWithStride (Stride 3) . mapStencil Edge (maxStencil (Sz 3)), Int (Stencil.hs:360-364 at scale)"),
+    "simpson": dict(dtype="f64", grid=(16384, 16385), stride=(1, 16), iterated=False,
+                    text="integrateWith simpsonsStencil (Dim 1) 16: Simpson's rule along the rows, Double, Fill 0 "
+                         "(Numeric/Integral.hs:99-135)"),
 }
-NPDT = {"f64": np.float64, "f32": np.float32, "u8": np.uint8}
+NPDT = {"f64": np.float64, "f32": np.float32, "u8": np.uint8, "i64": np.int64}
+SIMPSON_DX = 1.0 / 16.0
+
+
+def out_shape(name, shape):
+    """output extents of the workload on an input of `shape` (strideSize of the same-size mapStencil result)"""
+    st = WORKLOADS[name].get("stride")
+    return tuple(shape) if st is None else tuple((n - 1) // s + 1 for n, s in zip(shape, st))
+
+
+def bytes_per_cell(name, shape):
+    wl = WORKLOADS[name]
+    if "bpc" in wl:
+        return wl["bpc"]
+    item = np.dtype(NPDT[wl["dtype"]]).itemsize
+    return item * (float(np.prod(shape)) + float(np.prod(out_shape(name, shape)))) / float(np.prod(out_shape(name, shape)))
 
 
 def gauss7():
@@ -81,6 +102,10 @@ def oracle_spec(name):
         return "conv", dict(size=(7, 7), coeffs=np.outer(g, g).astype(np.float32).reshape(-1).tolist(), border="edge")
     if name == "life":
         return "life", dict(size=(3, 3), border="wrap")
+    if name == "pool3":
+        return "max", dict(size=(3, 3), border="edge", stride=(3, 3))
+    if name == "simpson":
+        return "int_simpson", dict(size=(1, 17), coeffs=[SIMPSON_DX], border="fill", fill=0.0, stride=(1, 16))
     raise KeyError(name)
 
 
@@ -101,6 +126,11 @@ def stencil_spec(name, M):
         return M.Edge, M.makeConvolutionStencilFromKernel(g.reshape(1, 7)), M.makeConvolutionStencilFromKernel(g.reshape(7, 1))
     if name == "life":
         return M.Wrap, M.lifeStencil
+    if name == "pool3":
+        return M.Edge, M.maxStencil(M.Sz(3, 3))
+    if name == "simpson":
+        from massiv_b200 import integral as I
+        return M.Fill(0.0), I.simpsonsStencil(np.float64(SIMPSON_DX), 1, 16)
     raise KeyError(name)
 
 
@@ -122,6 +152,8 @@ def synth_host(name, shape, seed=2020, first=0):
         return ((h >> np.uint64(11)).astype(np.float64) * 2.0 ** -53).reshape(shape)
     if dt == "f32":
         return ((h >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).reshape(shape)
+    if dt == "i64":
+        return (h >> np.uint64(11)).astype(np.int64).reshape(shape)
     return (h >> np.uint64(63)).astype(np.uint8).reshape(shape)
 
 
@@ -129,7 +161,7 @@ def synth_device(torch, name, shape, device, seed=2020, first=0):
     """same generator on the GPU (int64 arithmetic wraps like uint64; logical shifts emulated)"""
     n = int(np.prod(shape))
     dt = WORKLOADS[name]["dtype"]
-    tdt = {"f64": torch.float64, "f32": torch.float32, "u8": torch.uint8}[dt]
+    tdt = {"f64": torch.float64, "f32": torch.float32, "u8": torch.uint8, "i64": torch.int64}[dt]
     out = torch.empty(n, dtype=tdt, device=device)
     chunk = 1 << 26
 
@@ -150,6 +182,8 @@ def synth_device(torch, name, shape, device, seed=2020, first=0):
             out[a:b] = lsr(h, 11).to(torch.float64) * 2.0 ** -53
         elif dt == "f32":
             out[a:b] = lsr(h, 40).to(torch.float32) * 2.0 ** -24
+        elif dt == "i64":
+            out[a:b] = lsr(h, 11)
         else:
             out[a:b] = lsr(h, 63).to(torch.uint8)
         del x, z, h
@@ -251,7 +285,7 @@ def run_cpu(name, steps, warmup, threads=None):
         once()
     dt = time.perf_counter() - t0
     passes = inner if iterated else 1
-    cells = float(np.prod(shape)) * passes * steps
+    cells = float(np.prod(out_shape(wl, shape))) * passes * steps
     return dict(value=cells / dt / 1e9, seconds=dt, shape=list(shape), passes_per_step=passes, threads=threads)
 
 
@@ -307,14 +341,16 @@ def gpu_main(args):
     dev.set_stream(tstream.cuda_stream)
     spec = stencil_spec(name, M)
     border = spec[0]
-    cells = float(np.prod(grid))
+    stride = wl.get("stride")
+    ogrid = out_shape(name, grid)
+    cells = float(np.prod(ogrid))
     tdev = torch.device("cuda", local)
 
     # device-resident input (synthetic, generated on the GPU; rank r continues the index stream)
-    a_t = synth_device(torch, name, grid, tdev, first=rank * int(cells))
-    b_t = torch.empty_like(a_t)
+    a_t = synth_device(torch, name, grid, tdev, first=rank * int(np.prod(grid)))
+    b_t = torch.empty(ogrid, dtype=a_t.dtype, device=tdev)
     a = dev.wrap(a_t.data_ptr(), grid, npdt)
-    b = dev.wrap(b_t.data_ptr(), grid, npdt)
+    b = dev.wrap(b_t.data_ptr(), ogrid, npdt)
     dims = _abi.dims_array(grid)
 
     sharded = (world > 1 or os.environ.get("MASSIV_B200_BENCH_SHARDED")) and wl["iterated"] and name == "heat3d"
@@ -354,7 +390,9 @@ def gpu_main(args):
         def run(k):
             dev.check(L.mb_iterate_dev(dev.handle, C.byref(d), dims, C.c_void_p(a.ptr), C.c_void_p(b.ptr), k, C.byref(res)))
     else:
-        d = M.mapStencil(border, spec[1], a).desc()
+        dw = M.mapStencil(border, spec[1], a)
+        d = dw.desc(stride)
+        assert dw.size(stride) == ogrid, (dw.size(stride), ogrid)
 
         def run(k):
             for _ in range(k):
@@ -399,9 +437,10 @@ def gpu_main(args):
         peak, peak_src = load_peaks()
         per_launch_ms = ms / max(launches, 1)
         passes_per_launch = args.steps / max(launches, 1)
-        alg_bytes = cells * wl["bpc"] * passes_per_launch
+        bpc = bytes_per_cell(name, grid)
+        alg_bytes = cells * bpc * passes_per_launch
         if name == "gauss7sep" and launches == 2 * args.steps:
-            alg_bytes = cells * wl["bpc"]  # two-pass fallback: each launch moves one read + one write
+            alg_bytes = cells * bpc  # two-pass fallback: each launch moves one read + one write
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu:
@@ -413,8 +452,8 @@ def gpu_main(args):
             "metric": "stencil_gcells_per_s", "value": value, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
-            "config": {"workload": name, "description": wl["text"], "grid_per_gpu": list(grid),
-                       "l2": "inputs larger than L2" if cells * wl["bpc"] > 256e6 else "grid is L2-resident by definition of the workload",
+            "config": {"workload": name, "description": wl["text"], "grid_per_gpu": list(grid), "cells": "output cells" if stride else "cells",
+                       "l2": "inputs larger than L2" if cells * bpc > 256e6 else "grid is L2-resident by definition of the workload",
                        "kernel": kernel, "parallelism": f"slab{world}" if world > 1 else "single",
                        "halo_transport": L.mb_shard_transport(dev.handle).decode() if sharded else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -448,9 +487,12 @@ def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, 
     g = tuple(g)
     n = int(np.prod(g))
     nbytes = n * item
+    stride = wl.get("stride")
+    n_out = int(np.prod(out_shape(name, g)))
+    obytes = n_out * item
     hin, hout = C.c_void_p(), C.c_void_p()
     dev.check(L.mb_host_alloc(dev.handle, nbytes, C.byref(hin)))
-    dev.check(L.mb_host_alloc(dev.handle, nbytes, C.byref(hout)))
+    dev.check(L.mb_host_alloc(dev.handle, obytes, C.byref(hout)))
     src = np.ctypeslib.as_array(C.cast(hin, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(npdt).reshape(g)
     t = synth_device(torch, name, g, tdev, first=rank * n)  # fill the pinned input from the device generator
     torch.cuda.synchronize()
@@ -470,7 +512,7 @@ def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, 
         d = M.mapStencil(border, spec[1], src).desc()
         call, passes, cname = (lambda k: dev.check(L.mb_iterate(dev.handle, C.byref(d), dims, hin, hout, k))), steps, "mb_iterate"
     else:
-        d = M.mapStencil(border, spec[1], src).desc()
+        d = M.mapStencil(border, spec[1], src).desc(stride)
         call, passes, cname = (lambda k: dev.check(L.mb_run(dev.handle, C.byref(d), dims, hin, hout))), 1, "mb_run"
     for _ in range(3):
         call(2)  # warm-up: allocates the context's device scratch, touches the pinned pages
@@ -489,8 +531,8 @@ def measure_e2e(args, dev, M, name, grid, npdt, spec, world, rank, dist, torch, 
         dt = float(tt.item())
     dev.check(L.mb_host_free(dev.handle, hin))
     dev.check(L.mb_host_free(dev.handle, hout))
-    val = float(n) * world * passes * reps / dt / 1e9
-    return {"value": val, "unit": "Gcells/s", "h2d_bytes_per_step": nbytes / passes, "d2h_bytes_per_step": nbytes / passes,
+    val = float(n_out) * world * passes * reps / dt / 1e9
+    return {"value": val, "unit": "Gcells/s", "h2d_bytes_per_step": nbytes / passes, "d2h_bytes_per_step": obytes / passes,
             "grid_per_gpu": list(g), "passes_per_call": passes, "seconds_per_call": dt / reps, "call": cname,
             "timing": "host wall clock around the blocking C call, max over ranks"}
 

@@ -36,6 +36,11 @@ module Data.Massiv.Array.Stencil.B200
   , lifeStencil
   , sobelMagnitude
   , assumeFinite
+    -- * Integral approximation (Data.Massiv.Array.Numeric.Integral)
+  , midpointStencil
+  , trapezoidStencil
+  , simpsonsStencil
+  , integrateWithB200
     -- * Application
   , computeB200
   , mapStencilB200
@@ -102,6 +107,7 @@ withDeviceB200 ordinal = bracket open close
     close (DeviceB200 p) = () <$ c_mb_ctx_destroy p
 
 data Kind = KId | KSum | KProduct | KAvg | KMax | KMin | KConv | KCorr | KTaps | KLife | KMag2
+          | KIntMidpoint | KIntTrapezoid | KIntSimpson
   deriving (Eq, Enum)
 
 -- | Element types with a device representation (Storable sizes, Bool is 4 bytes).
@@ -169,6 +175,28 @@ lifeStencil = StencilB200 KLife (Sz (3 A.:. 3)) (1 A.:. 1) Nothing Nothing 0
 -- as one fused pass (massiv-bench Data.Massiv.Bench.Sobel lines 39-44).
 sobelMagnitude :: (Floating e, Index ix) => Array S ix e -> Array S ix e -> StencilB200 ix e
 sobelMagnitude kx ky = (makeConvolutionStencilFromKernel kx) { sbKind = KMag2, sbCoeffs2 = Just ky }
+
+-- | The rule stencils of Data.Massiv.Array.Numeric.Integral (lines 54-118), reified: size 1 in every
+-- dimension but @dim@, centre 0, @dx@ carried as the single coefficient.  The device evaluates
+-- them in the reference's operation order (e.g. @(dx / 2) * ((g 0 + 2 * g 1 + ..) + g n)@).
+midpointStencil, trapezoidStencil, simpsonsStencil
+  :: (Fractional e, ElemB200 e, Index ix) => e -> A.Dim -> Int -> StencilB200 ix e
+midpointStencil dx dim k = ruleStencil KIntMidpoint dx dim k
+trapezoidStencil dx dim n = ruleStencil KIntTrapezoid dx dim (n + 1)
+simpsonsStencil dx dim n
+  | odd n = error $ "Number of sample points for Simpson's rule stencil should be even, but received: " ++ show n
+  | otherwise = ruleStencil KIntSimpson dx dim (n + 1)
+
+ruleStencil :: (ElemB200 e, Index ix) => Kind -> e -> A.Dim -> Int -> StencilB200 ix e
+ruleStencil kind dx dim len =
+  StencilB200 kind (Sz (A.setDim' (A.pureIndex 1) dim len)) A.zeroIndex (Just (A.computeAs A.S (A.singleton dx))) Nothing 0
+
+-- | @integrateWith@ (Integral.hs 121-135): @computeWithStride (Stride nsz) . mapStencil (Fill 0) (stencil dim n)@.
+integrateWithB200
+  :: (Fractional e, ElemB200 e, Index ix)
+  => DeviceB200 -> (A.Dim -> Int -> StencilB200 ix e) -> A.Dim -> Int -> Array S ix e -> IO (Array S ix e)
+integrateWithB200 dev stencil dim n =
+  computeWithStrideB200 dev (A.Stride (A.setDim' (A.pureIndex 1) dim n)) (Fill 0) (stencil dim n)
 
 -- | Promise finite inputs: zero coefficients may be skipped (bit-identical for finite data).
 assumeFinite :: StencilB200 ix e -> StencilB200 ix e
