@@ -93,6 +93,8 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
     if (st != -1) return st;
     st = launch_linescan(c, dp, d_in, d_out, range);
     if (st != -1) return st;
+    st = launch_direct2d(c, dp, d_in, d_out, range);
+    if (st != -1) return st;
   }
   return launch_generic(c, dp, d_in, d_out, range);
 }

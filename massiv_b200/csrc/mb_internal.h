@@ -117,6 +117,7 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
 
 // kernel families (each returns MB_OK, an error, or -1 for "not applicable, try the next one")
 int launch_linescan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
+int launch_direct2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
 int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
