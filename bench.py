@@ -239,6 +239,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_traffic(name, kernel, grid):
+    """measured DRAM bytes per launch of the dominant kernel (ncu capture summarised under profiles/), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+        if t and t["kernel"] == kernel and list(t["grid"]) == list(grid):
+            return t["bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -457,7 +468,7 @@ def gpu_main(args):
                        "kernel": kernel, "parallelism": f"slab{world}" if world > 1 else "single",
                        "halo_transport": L.mb_shard_transport(dev.handle).decode() if sharded else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": kernel,
+                         "traffic": load_traffic(name, kernel, grid) if world == 1 else None, "peak_source": peak_src, "kernel": kernel,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
