@@ -84,7 +84,7 @@ foreign import ccall safe "mb_iterate"     c_mb_iterate
 data MbDesc
 
 mbDescBytes :: Int
-mbDescBytes = 16 + 5 * 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8
+mbDescBytes = 16 + 5 * 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8  -- ... flags, n_post (4 + 4), post pointer: 272
 
 -- ---------------------------------------------------------------------------------------------
 

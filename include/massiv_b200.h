@@ -85,6 +85,34 @@ typedef enum mb_kind {
 /* Border (Core/Index.hs:159-195) resolved by handleBorderIndex (Core/Index.hs:236-253) */
 typedef enum mb_border { MB_FILL = 0, MB_WRAP, MB_EDGE, MB_REFLECT, MB_CONTINUE } mb_border;
 
+/* Post-maps: `fmap f` over the stencil's result (Functor (Stencil ix e), Stencil/Internal.hs:36-41,
+ * 70-83) or over the windowed array (Functor (Array DW ix), Delayed/Windowed.hs:78-84), and the
+ * unary methods of the Num / Fractional / Floating instances of Stencil that are defined as fmap
+ * (Stencil/Internal.hs:114-146), for the f whose result is fixed by IEEE-754 / two's complement —
+ * so that it stays bit-identical.  Applied in order to every output cell.  c is `operand`. */
+typedef enum mb_post {
+  MB_POST_NEGATE = 1, /* negate                                                        */
+  MB_POST_ABS,        /* abs      (minBound stays minBound for integers)               */
+  MB_POST_SIGNUM,     /* signum   (+-0 and NaN map to themselves for Float/Double)     */
+  MB_POST_SQUARE,     /* (^2)     x * x                                                */
+  MB_POST_ADD,        /* (+ c)    x + c                                                */
+  MB_POST_SUB,        /* subtract c: x - c                                             */
+  MB_POST_RSUB,       /* (c -)    c - x                                                */
+  MB_POST_MUL,        /* (* c)    x * c                                                */
+  MB_POST_MIN,        /* min x c = if x <= c then x else c     (GHC.Classes default)   */
+  MB_POST_MAX,        /* max x c = if x <= c then c else x                             */
+  MB_POST_DIV,        /* (/ c)    x / c      Float / Double only from here on          */
+  MB_POST_RDIV,       /* (c /)    c / x                                                */
+  MB_POST_RECIP,      /* recip    1 / x                                                */
+  MB_POST_SQRT        /* sqrt                                                          */
+} mb_post;
+#define MB_MAX_POST 8
+typedef struct mb_post_op {
+  int32_t op;         /* mb_post */
+  int32_t reserved;
+  uint8_t operand[8]; /* c in the element type (native-endian, first sizeof(elem) bytes) */
+} mb_post_op;
+
 #define MB_FLAG_MAG2_CORR 1u     /* MAG2 sub-stencils are correlations                         */
 #define MB_FLAG_ASSUME_FINITE 2u /* inputs are finite: zero coefficients may be skipped        */
 
@@ -111,7 +139,8 @@ typedef struct mb_stencil_desc {
   int64_t ntaps;                 /* TAPS                                                       */
   const int64_t *tap_offsets;    /* TAPS: ntaps*rank source offsets in application order       */
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t n_post;               /* number of post-maps, <= MB_MAX_POST                       */
+  const mb_post_op *post;        /* applied in order to every result                          */
 } mb_stencil_desc;
 
 typedef struct mb_ctx mb_ctx;

@@ -36,6 +36,29 @@ SYMBOLS = [
 ]
 
 
+POSTS = {"negate": 1, "abs": 2, "signum": 3, "square": 4, "add": 5, "sub": 6, "rsub": 7, "mul": 8, "min": 9, "max": 10,
+         "div": 11, "rdiv": 12, "recip": 13, "sqrt": 14}
+MAX_POST = 8
+
+
+class PostOp(C.Structure):
+    """mb_post_op: one fmap'ed function; the operand c lives in the element type"""
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("operand", C.c_uint8 * 8)]
+
+
+def post_array(post, npdt):
+    """[(name,) | (name, c), ...] -> ctypes array of PostOp"""
+    import numpy as _np
+    arr = (PostOp * max(1, len(post)))()
+    for i, item in enumerate(post):
+        name, c = (item[0], item[1] if len(item) > 1 else 0)
+        arr[i].op = POSTS[name]
+        raw = _np.array([c]).astype(npdt).tobytes()
+        for j, b in enumerate(raw):
+            arr[i].operand[j] = b
+    return arr
+
+
 class StencilDesc(C.Structure):
     """mb_stencil_desc"""
     _fields_ = [("kind", C.c_int32), ("elem", C.c_int32), ("rank", C.c_int32), ("border", C.c_int32),
@@ -43,7 +66,7 @@ class StencilDesc(C.Structure):
                 ("pad_lo", C.c_int64 * MAX_RANK), ("pad_hi", C.c_int64 * MAX_RANK),
                 ("stride", C.c_int64 * MAX_RANK), ("fill", C.c_uint8 * 8),
                 ("coeffs", C.c_void_p), ("coeffs2", C.c_void_p), ("ntaps", C.c_int64),
-                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p)]
 
 
 MAX_HALO = 8

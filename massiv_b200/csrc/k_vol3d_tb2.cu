@@ -341,7 +341,7 @@ static bool star_only(const Plan &p) {
 
 // descriptor-only eligibility (decides how many ghost planes a sharded slab carries)
 bool tb2_desc_eligible(const mb_stencil_desc *d) {
-  if (!d || d->rank != 3 || (d->kind != MB_CONV && d->kind != MB_CORR) || !d->coeffs) return false;
+  if (!d || d->rank != 3 || (d->kind != MB_CONV && d->kind != MB_CORR) || !d->coeffs || d->n_post) return false;
   if (!(d->flags & MB_FLAG_ASSUME_FINITE) || d->border != MB_FILL) return false;
   if (d->elem != MB_F32 && d->elem != MB_F64) return false;
   const int es = d->elem == MB_F32 ? 4 : 8;
@@ -357,7 +357,7 @@ bool tb2_desc_eligible(const mb_stencil_desc *d) {
 
 // May two steps of this single-step plan be fused?  (the plan describes ONE application)
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
-  if (!c->tb2 || c->force_generic || c->no_tma) return false;
+  if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return false;
   if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return false;
   if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
   if (p.border != MB_FILL) return false;

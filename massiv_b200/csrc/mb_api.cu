@@ -55,6 +55,7 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
   key.append((const char *)p.tap_off.data(), p.tap_off.size() * sizeof(int32_t));
   key.append((const char *)p.c1.data(), p.c1.size());
   key.append((const char *)p.c2.data(), p.c2.size());
+  key.append((const char *)p.post.data(), p.post.size() * sizeof(mb_post_op));
   auto it = c->plans.find(key);
   if (it != c->plans.end()) { *out = it->second; return MB_OK; }
   if (c->plans.size() > 256) c->plans.clear();  // bounded; shared_ptrs keep in-flight plans alive
@@ -82,8 +83,20 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
 
 // Kernel-family dispatch.  Order: most specialised first; each family answers -1 when the plan is
 // outside what it covers.  The generic kernel covers everything.
+static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+
 int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   if (dp.p.out_elems == 0) return MB_OK;
+  int st = launch_family(c, dp, d_in, d_out, range);
+  if (st || dp.p.post.empty()) return st;
+  // post-maps run as an in-place pass over what the stencil kernel just wrote (same stream)
+  const char *family = c->last_kernel;
+  st = launch_post(c, dp.p, d_out, range);
+  c->last_kernel = family;
+  return st;
+}
+
+static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   if (!c->force_generic) {
     int st = range ? -1 : launch_life(c, dp, d_in, d_out);  // the Life kernels produce whole arrays
     if (st != -1) return st;
@@ -128,7 +141,7 @@ static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t
   int st = get_dev_plan(c, desc, dims, &dp);
   if (st) return st;
   if (!dp->p.same_shape()) return fail(c, MB_ERR_SIZE_MISMATCH, "iterate needs output size == input size");
-  if (!c->force_generic) {
+  if (!c->force_generic && dp->p.post.empty()) {
     st = life_iterate(c, *dp, a, b, n_steps, result);
     if (st != -1) return st;
   }
@@ -171,7 +184,7 @@ static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_de
   if ((st = get_dev_plan(c, s, dims, &p2))) return st;
   if (!p1->p.same_shape() || !p2->p.same_shape())
     return fail(c, MB_ERR_SIZE_MISMATCH, "separable passes must be mapStencil-shaped (same size in and out)");
-  if (!c->force_generic) {
+  if (!c->force_generic && p1->p.post.empty() && p2->p.post.empty()) {
     st = run_sep2_fused(c, *p1, *p2, d_in, d_out);
     if (st != -1) return st;
   }

@@ -38,6 +38,7 @@ struct Plan {
   std::vector<int32_t> tap_off;          // ntaps * rank, application order
   std::vector<uint8_t> c1, c2;           // ntaps coefficients each (elem bytes), may be empty
   uint8_t fill[8] = {0};
+  std::vector<mb_post_op> post;          // fmap'ed functions applied to every result, in order
   int64_t in_elems = 0, out_elems = 0;
   bool dense = false;                    // taps form the full [0,size) window (fold/conv/corr/mag2)
   bool descending = false;               // dense taps visited with descending offsets (conv)
@@ -118,6 +119,7 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
 // kernel families (each returns MB_OK, an error, or -1 for "not applicable, try the next one")
 int launch_linescan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
 int launch_direct2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
+int launch_post(Ctx *c, const Plan &p, void *d_out, const OuterRange *range);  // in-place post-maps over the output
 int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);

@@ -104,6 +104,14 @@ static int validate(const mb_stencil_desc *d, std::string *err) {
     }
     default: return bad(MB_ERR_INVALID_DESC, "unknown stencil kind");
   }
+  if (d->n_post > MB_MAX_POST) return bad(MB_ERR_UNSUPPORTED, "too many post-maps");
+  if (d->n_post > 0 && !d->post) return bad(MB_ERR_INVALID_DESC, "missing post-map list");
+  for (uint32_t i = 0; i < d->n_post; ++i) {
+    const int op = d->post[i].op;
+    if (op < MB_POST_NEGATE || op > MB_POST_SQRT) return bad(MB_ERR_INVALID_DESC, "unknown post-map");
+    if (op >= MB_POST_DIV && !is_float(d->elem)) return bad(MB_ERR_UNSUPPORTED, "post-map needs Fractional / Floating e");
+    if (d->elem == MB_BOOL32) return bad(MB_ERR_UNSUPPORTED, "Bool is not Num");
+  }
   return MB_OK;
 }
 
@@ -113,6 +121,7 @@ int plan_geometry(const mb_stencil_desc *d, const int64_t *in_dims, Plan *p, std
   p->kind = d->kind; p->elem = d->elem; p->rank = d->rank; p->border = d->border; p->flags = d->flags;
   p->esize = elem_size(d->elem);
   std::memcpy(p->fill, d->fill, 8);
+  if (d->n_post) p->post.assign(d->post, d->post + d->n_post);
   const bool mag_corr = d->kind == MB_MAG2 && (d->flags & MB_FLAG_MAG2_CORR);
   p->in_elems = 1; p->out_elems = 1;
   for (int i = 0; i < d->rank; ++i) {

@@ -99,6 +99,7 @@ class Stencil:
     flags: int = 0
     scalar_size: Optional[int] = None
     along: Optional[Tuple[int, int]] = None    # (Dim, length): size 1 everywhere but along Dim (integral rules)
+    post: Tuple[tuple, ...] = ()               # fmap'ed functions applied to the result, in order: (name[, c])
 
     def _resolved(self, rank: int) -> "Stencil":
         if self.along is not None and self.size is None:
@@ -106,30 +107,86 @@ class Stencil:
             if not 1 <= dim <= rank:   # setDim' throws IndexDimensionException
                 raise IndexError(f"IndexDimensionException: (Dim {dim}) for an index of rank {rank}")
             size = tuple(length if i == rank - dim else 1 for i in range(rank))   # Dim 1 is the innermost
-            return Stencil(self.kind, size, None, self.coeffs, self.coeffs2, self.taps, self.flags)
+            return Stencil(self.kind, size, None, self.coeffs, self.coeffs2, self.taps, self.flags, post=self.post)
         if self.size is not None:
             if len(self.size) != rank:
                 raise ValueError(f"stencil of rank {len(self.size)} applied to an array of rank {rank}")
             return self
-        return Stencil(self.kind, (self.scalar_size,) * rank, None, self.coeffs, self.coeffs2, self.taps, self.flags)
+        return Stencil(self.kind, (self.scalar_size,) * rank, None, self.coeffs, self.coeffs2, self.taps, self.flags, post=self.post)
 
     def assumeFinite(self) -> "Stencil":
         """Device-path extension: promise finite inputs so zero coefficients may be skipped
         (bit-identical for finite data; see MB_FLAG_ASSUME_FINITE)."""
         return Stencil(self.kind, self.size, self.center, self.coeffs, self.coeffs2, self.taps,
-                       self.flags | _abi.FLAG_ASSUME_FINITE, self.scalar_size, self.along)
+                       self.flags | _abi.FLAG_ASSUME_FINITE, self.scalar_size, self.along, self.post)
+
+    # ---- Functor / Num / Fractional / Floating (Stencil/Internal.hs:36-41, 114-146) --------------
+    # `fmap f` for the f whose result is exactly specified (include/massiv_b200.h: mb_post); anything
+    # else is a closure and stays on massiv's CPU path.
+    def fmap(self, name: str, c=None) -> "Stencil":
+        """``fmap f stencil`` with f named: "negate", "abs", "signum", "square" (^2), "recip", "sqrt", or with a
+        constant c: "add" (+ c), "sub" (subtract c), "rsub" (c -), "mul" (* c), "div" (/ c), "rdiv" (c /), "min", "max"."""
+        if name not in _abi.POSTS:
+            raise NotImplementedError(f"fmap {name}: not an exactly specified post-map; closures cannot run on the device")
+        if self.kind == "life" or len(self.post) >= _abi.MAX_POST:
+            raise NotImplementedError("too many post-maps, or a rule stencil")
+        item = (name,) if c is None else (name, c)
+        return Stencil(self.kind, self.size, self.center, self.coeffs, self.coeffs2, self.taps, self.flags,
+                       self.scalar_size, self.along, self.post + (item,))
+
+    def __neg__(self):
+        return self.fmap("negate")
+
+    def __abs__(self):
+        return self.fmap("abs")
+
+    def signum(self):
+        return self.fmap("signum")
+
+    def recip(self):
+        return self.fmap("recip")
+
+    def sqrt(self):
+        return self.fmap("sqrt")
+
+    def __add__(self, c):   # stencil + fromInteger c  ==  liftA2 (+) stencil (pure c): same size and centre
+        return self.fmap("add", c) if np.isscalar(c) else NotImplemented
+
+    __radd__ = __add__      # IEEE / modular addition commutes
+
+    def __sub__(self, c):
+        return self.fmap("sub", c) if np.isscalar(c) else NotImplemented
+
+    def __rsub__(self, c):
+        return self.fmap("rsub", c) if np.isscalar(c) else NotImplemented
+
+    def __mul__(self, c):
+        return self.fmap("mul", c) if np.isscalar(c) else NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        return self.fmap("div", c) if np.isscalar(c) else NotImplemented
+
+    def __rtruediv__(self, c):
+        return self.fmap("rdiv", c) if np.isscalar(c) else NotImplemented
 
     # Num / Floating instances (Stencil/Internal.hs:114-174) — only the Sobel-magnitude shape
     # `sqrt (fmap (^2) a + fmap (^2) b)` lowers to a device kernel (MB_MAG2).
     def __pow__(self, n):
-        if n != 2 or self.kind not in ("conv", "corr"):
-            raise NotImplementedError("only `fmap (^2)` of a FromKernel stencil lowers to the device")
-        return _Squared(self)
+        if n != 2:
+            raise NotImplementedError("only `fmap (^2)` lowers to the device")
+        if self.kind in ("conv", "corr") and not self.post:
+            return _Squared(self)   # may still become sqrt (a^2 + b^2); resolves to fmap (^2) otherwise
+        return self.fmap("square")
 
 
 @dataclass(frozen=True)
 class _Squared:
     s: Stencil
+
+    def _resolved(self, rank: int) -> "Stencil":   # used on its own: plain fmap (^2)
+        return self.s.fmap("square")._resolved(rank)
 
     def __add__(self, other):
         if not isinstance(other, _Squared):
@@ -144,7 +201,12 @@ class _SumSq:
 
 
 def sqrt(x):
-    """``sqrt`` of the Floating (Stencil ix e) instance, for ``sqrt(sx**2 + sy**2)``."""
+    """``sqrt`` of the Floating (Stencil ix e) instance: ``sqrt(sx**2 + sy**2)`` fuses into one kernel
+    (MB_MAG2); ``sqrt stencil`` is ``fmap sqrt``."""
+    if isinstance(x, Stencil):
+        return x.fmap("sqrt")
+    if isinstance(x, _Squared):
+        return x.s.fmap("square").fmap("sqrt")
     if not isinstance(x, _SumSq):
         raise NotImplementedError("only sqrt(a**2 + b**2) of two FromKernel stencils lowers to the device")
     a, b = x.a, x.b
@@ -449,8 +511,16 @@ class DW:
             keep.append(offs)
             d.ntaps, d.tap_offsets = offs.shape[0], offs.ctypes.data
         d.flags = st.flags
+        if st.post:
+            pa = _abi.post_array(st.post, npdt)
+            keep.append(pa)
+            d.n_post, d.post = len(st.post), C.cast(pa, C.c_void_p)
         d._keep = keep  # the descriptor owns the buffers its pointers refer to
         return d
+
+    def fmap(self, name: str, c=None) -> "DW":
+        """Functor (Array DW ix) (Delayed/Windowed.hs:78-84): map over the windowed array before it is computed"""
+        return DW(self.padding, self.stencil.fmap(name, c), self.arr, self.elem)
 
     def size(self, stride=None) -> Ix:
         d = self.desc(stride)

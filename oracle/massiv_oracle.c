@@ -344,6 +344,80 @@ static void free_plan(mo_plan *p) { free(p->tap_off); free(p->tap_lin); }
 #undef SUF
 #undef ACC
 
+/* ---- post-maps: fmap f over the results ------------------------------------------------------- */
+#define POST_FLOAT(T, NAME, SQRT)                                                              \
+  static T NAME(int op, T x, T c) {                                                            \
+    switch (op) {                                                                              \
+      case MO_POST_NEGATE: return -x;                 /* negateFloat#: sign flip */            \
+      case MO_POST_ABS: return x == 0 ? (T)0 : (x > 0 ? x : -x); /* GHC.Float abs */           \
+      case MO_POST_SIGNUM: return x > 0 ? (T)1 : (x < 0 ? (T)-1 : x); /* GHC.Float signum */   \
+      case MO_POST_SQUARE: return x * x;              /* x ^ 2 */                              \
+      case MO_POST_ADD: return x + c;                                                          \
+      case MO_POST_SUB: return x - c;                                                          \
+      case MO_POST_RSUB: return c - x;                                                         \
+      case MO_POST_MUL: return x * c;                                                          \
+      case MO_POST_MIN: return x <= c ? x : c;        /* GHC.Classes: min x y = if x <= y then x else y */ \
+      case MO_POST_MAX: return x <= c ? c : x;        /*              max x y = if x <= y then y else x */ \
+      case MO_POST_DIV: return x / c;                                                          \
+      case MO_POST_RDIV: return c / x;                                                         \
+      case MO_POST_RECIP: return (T)1 / x;            /* recip x = 1.0 / x */                  \
+      default: return SQRT(x);                                                                 \
+    }                                                                                          \
+  }
+POST_FLOAT(float, post_f32, sqrtf)
+POST_FLOAT(double, post_f64, sqrt)
+
+#define POST_INT(T, U, NAME)                                                                   \
+  static T NAME(int op, T x, T c) {                                                            \
+    switch (op) { /* fixed-width wraparound: computed in the unsigned type */                  \
+      case MO_POST_NEGATE: return (T)((U)0 - (U)x);                                            \
+      case MO_POST_ABS: return x >= 0 ? x : (T)((U)0 - (U)x); /* abs minBound = minBound */    \
+      case MO_POST_SIGNUM: return x > 0 ? (T)1 : (x < 0 ? (T)((U)0 - (U)1) : (T)0);            \
+      case MO_POST_SQUARE: return (T)((U)x * (U)x);                                            \
+      case MO_POST_ADD: return (T)((U)x + (U)c);                                               \
+      case MO_POST_SUB: return (T)((U)x - (U)c);                                               \
+      case MO_POST_RSUB: return (T)((U)c - (U)x);                                              \
+      case MO_POST_MUL: return (T)((U)x * (U)c);                                               \
+      case MO_POST_MIN: return x <= c ? x : c;                                                 \
+      default: return x <= c ? c : x;                                                          \
+    }                                                                                          \
+  }
+POST_INT(uint8_t, uint32_t, post_u8)
+POST_INT(int8_t, uint32_t, post_i8)
+POST_INT(uint16_t, uint32_t, post_u16)
+POST_INT(int16_t, uint32_t, post_i16)
+POST_INT(uint32_t, uint32_t, post_u32)
+POST_INT(int32_t, uint32_t, post_i32)
+POST_INT(uint64_t, uint64_t, post_u64)
+POST_INT(int64_t, uint64_t, post_i64)
+
+static int apply_post(const mo_desc *d, void *out, int64_t n) {
+  if (d->n_post > MO_MAX_POST) return MO_ERR_UNSUPPORTED;
+  if (!d->post) return MO_ERR_INVALID_DESC;
+  if (d->elem == MO_BOOL32) return MO_ERR_UNSUPPORTED;
+  for (uint32_t k = 0; k < d->n_post; ++k) {
+    const int op = d->post[k].op;
+    if (op < MO_POST_NEGATE || op > MO_POST_SQRT) return MO_ERR_INVALID_DESC;
+    if (op >= MO_POST_DIV && !is_float(d->elem)) return MO_ERR_UNSUPPORTED;
+#define RUN(T, F) { T c; memcpy(&c, d->post[k].operand, sizeof(T)); T *o = (T *)out; for (int64_t i = 0; i < n; ++i) o[i] = F(op, o[i], c); }
+    switch (d->elem) {
+      case MO_U8: RUN(uint8_t, post_u8) break;
+      case MO_I8: RUN(int8_t, post_i8) break;
+      case MO_U16: RUN(uint16_t, post_u16) break;
+      case MO_I16: RUN(int16_t, post_i16) break;
+      case MO_U32: RUN(uint32_t, post_u32) break;
+      case MO_I32: RUN(int32_t, post_i32) break;
+      case MO_U64: RUN(uint64_t, post_u64) break;
+      case MO_I64: RUN(int64_t, post_i64) break;
+      case MO_F32: RUN(float, post_f32) break;
+      case MO_F64: RUN(double, post_f64) break;
+      default: return MO_ERR_INVALID_DESC;
+    }
+#undef RUN
+  }
+  return MO_OK;
+}
+
 int mo_apply(const mo_desc *d, const int64_t *in_dims, const void *in, void *out, int nthreads) {
   mo_plan p;
   int st = build_plan(d, in_dims, &p);
@@ -362,6 +436,11 @@ int mo_apply(const mo_desc *d, const int64_t *in_dims, const void *in, void *out
     case MO_F32: apply_f32(&p, (const float *)in, (float *)out, nthreads); break;
     case MO_F64: apply_f64(&p, (const double *)in, (double *)out, nthreads); break;
     default: st = MO_ERR_INVALID_DESC;
+  }
+  if (!st && d->n_post) {
+    int64_t n = 1;
+    for (int i = 0; i < d->rank; ++i) n *= p.out_dims[i];
+    st = apply_post(d, out, n);
   }
   free_plan(&p);
   return st;

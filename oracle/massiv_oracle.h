@@ -61,6 +61,15 @@ enum { MO_FILL = 0, MO_WRAP, MO_EDGE, MO_REFLECT, MO_CONTINUE };
 #define MO_FLAG_MAG2_CORR 1u   /* MAG2 sub-stencils are correlations instead of convolutions */
 #define MO_FLAG_NO_FAST (1u << 31) /* oracle only: disable the vectorised interior loop nest */
 
+/* `fmap f` over the stencil's results: rmapStencil (Stencil/Internal.hs:70-83), the Num / Fractional /
+ * Floating methods defined through it (:114-146), Functor (Array DW ix) (Delayed/Windowed.hs:78-84).
+ * Only f with an exactly specified result; semantics are GHC's Prelude instances (GHC.Float, GHC.Num,
+ * GHC.Classes default min/max).  No reference test pins these beyond the Prelude's own definitions. */
+enum { MO_POST_NEGATE = 1, MO_POST_ABS, MO_POST_SIGNUM, MO_POST_SQUARE, MO_POST_ADD, MO_POST_SUB, MO_POST_RSUB,
+       MO_POST_MUL, MO_POST_MIN, MO_POST_MAX, MO_POST_DIV, MO_POST_RDIV, MO_POST_RECIP, MO_POST_SQRT };
+#define MO_MAX_POST 8
+typedef struct mo_post_op { int32_t op; int32_t reserved; uint8_t operand[8]; } mo_post_op;
+
 /* Field-for-field the same layout as mb_stencil_desc in include/massiv_b200.h so the tests can
  * hand one ctypes structure to both sides; the two headers are otherwise independent. */
 typedef struct mo_desc {
@@ -76,7 +85,8 @@ typedef struct mo_desc {
   int64_t ntaps;                 /* TAPS only                                            */
   const int64_t *tap_offsets;    /* TAPS only: ntaps*rank source offsets, application order */
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t n_post;               /* post-maps (fmap f over the results), applied in order        */
+  const struct mo_post_op *post;
 } mo_desc;
 
 /* repaired index of handleBorderIndex for one dimension; *fill set to 1 when a Fill border

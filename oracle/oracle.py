@@ -43,13 +43,36 @@ class OracleError(RuntimeError):
         self.status = status
 
 
+POSTS = {"negate": 1, "abs": 2, "signum": 3, "square": 4, "add": 5, "sub": 6, "rsub": 7, "mul": 8, "min": 9, "max": 10,
+         "div": 11, "rdiv": 12, "recip": 13, "sqrt": 14}
+MAX_POST = 8
+
+
+class PostOp(C.Structure):
+    """mb_post_op: one fmap'ed function; the operand c lives in the element type"""
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("operand", C.c_uint8 * 8)]
+
+
+def post_array(post, npdt):
+    """[(name,) | (name, c), ...] -> ctypes array of PostOp"""
+    import numpy as _np
+    arr = (PostOp * max(1, len(post)))()
+    for i, item in enumerate(post):
+        name, c = (item[0], item[1] if len(item) > 1 else 0)
+        arr[i].op = POSTS[name]
+        raw = _np.array([c]).astype(npdt).tobytes()
+        for j, b in enumerate(raw):
+            arr[i].operand[j] = b
+    return arr
+
+
 class _Desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("elem", C.c_int32), ("rank", C.c_int32), ("border", C.c_int32),
                 ("size", C.c_int64 * MAX_RANK), ("center", C.c_int64 * MAX_RANK),
                 ("pad_lo", C.c_int64 * MAX_RANK), ("pad_hi", C.c_int64 * MAX_RANK),
                 ("stride", C.c_int64 * MAX_RANK), ("fill", C.c_uint8 * 8),
                 ("coeffs", C.c_void_p), ("coeffs2", C.c_void_p), ("ntaps", C.c_int64),
-                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p)]
 
 
 def build(force: bool = False) -> str:
@@ -112,7 +135,7 @@ class _Built:
 
 def make_desc(kind: str, elem: str, rank: int, *, size, center=None, pad_lo=None, pad_hi=None,
               border="fill", fill=0, stride=None, coeffs=None, coeffs2=None, taps=None,
-              flags: int = 0) -> _Built:
+              flags: int = 0, post=None) -> _Built:
     d = _Desc()
     keep = []
     d.kind, d.elem, d.rank, d.border = KINDS[kind], ELEMS[elem], rank, BORDERS[border]
@@ -147,6 +170,10 @@ def make_desc(kind: str, elem: str, rank: int, *, size, center=None, pad_lo=None
         d.ntaps = offs.shape[0]
         d.tap_offsets = offs.ctypes.data
     d.flags = flags
+    if post:
+        pa = post_array(post, npdt)
+        keep.append(pa)
+        d.n_post, d.post = len(post), C.cast(pa, C.c_void_p)
     return _Built(d, keep)
 
 

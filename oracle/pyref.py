@@ -185,6 +185,47 @@ def mag2(s1: Stencil, s2: Stencil, dt) -> Stencil:  # sqrt (fmap (^2) s1 + fmap 
     return fmap(lambda v: dt.type(np.sqrt(v)), lift2(lambda a, b: dt.type(a + b), fmap(sq, s1), fmap(sq, s2)))
 
 
+def post_fn(name: str, c, dt):
+    """the Prelude function behind one post-map (GHC.Float / GHC.Num / GHC.Classes), in dtype dt"""
+    t = dt.type
+    isf = dt.kind == "f"
+
+    def wrap(v):  # fixed-width integers wrap
+        if isf:
+            return t(v)
+        bits = 8 * dt.itemsize
+        v = int(v) & ((1 << bits) - 1)
+        if dt.kind == "i" and v >= 1 << (bits - 1):
+            v -= 1 << bits
+        return t(v)
+    ex = (lambda x: x) if isf else int
+    cc = t(c) if c is not None else None
+    table = {
+        "negate": lambda x: t(-x) if isf else wrap(-int(x)),
+        "abs": lambda x: (t(0) if x == 0 else (x if x > 0 else t(-x))) if isf else (x if x >= 0 else wrap(-int(x))),
+        "signum": lambda x: (t(1) if x > 0 else (t(-1) if x < 0 else x)) if isf else (t(1) if x > 0 else (wrap(-1) if x < 0 else t(0))),
+        "square": lambda x: wrap(ex(x) * ex(x)),
+        "add": lambda x: wrap(ex(x) + ex(cc)),
+        "sub": lambda x: wrap(ex(x) - ex(cc)),
+        "rsub": lambda x: wrap(ex(cc) - ex(x)),
+        "mul": lambda x: wrap(ex(x) * ex(cc)),
+        "min": lambda x: x if x <= cc else cc,
+        "max": lambda x: cc if x <= cc else x,
+        "div": lambda x: t(x / cc),
+        "rdiv": lambda x: t(cc / x),
+        "recip": lambda x: t(t(1) / x),
+        "sqrt": lambda x: t(np.sqrt(x)),
+    }
+    return table[name]
+
+
+def with_post(st: Stencil, post, dt) -> Stencil:
+    """fmap f1 . fmap f2 ... in application order"""
+    for item in post:
+        st = fmap(post_fn(item[0], item[1] if len(item) > 1 else None, dt), st)
+    return st
+
+
 def life_stencil() -> Stencil:  # GameOfLife.hs:15-36
     u8 = np.uint8
 
