@@ -195,6 +195,72 @@ static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_de
   return launch_plan(c, *p2, d_tmp, d_out, nullptr);
 }
 
+// Host -> host single pass as a three-stage pipeline over chunks of the outermost dimension: the input
+// travels up in chunks on the copy stream, a chunk of output planes is computed as soon as the input
+// planes it reads (its own plus the stencil's reach) have landed, and leaves on a third stream while the
+// next chunk is computed.  PCIe is full duplex, so the two copies overlap each other as well as the
+// kernel.  -1: not worth it / not applicable (small arrays, strided evaluation): the caller runs serially.
+int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out, void *d_in, void *d_out) {
+  const Plan &p = dp.p;
+  if (!c->pipeline || !p.unit_stride() || p.out_elems == 0 || p.in_elems == 0) return -1;
+  const size_t ib = (size_t)p.in_elems * p.esize, ob = (size_t)p.out_elems * p.esize;
+  const int64_t D = p.in_dims[0], OD = p.out_dims[0];
+  int nch = (int)std::min<size_t>(16, (ib + ob) / ((size_t)96 << 20));
+  const int64_t reach = std::max<int64_t>(1, std::max(-(p.shift[0] + p.min_off[0]), p.shift[0] + p.max_off[0]));
+  while (nch > 1 && (OD / nch < 4 * (reach + 1) || D / nch < 4 * (reach + 1))) --nch;
+  if (nch < 2) return -1;
+  if (!c->out_stream && cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return -1; }
+  while ((int)c->pipe_events.size() < 2 * 16) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+    c->pipe_events.push_back(e);
+  }
+  size_t in_plane = (size_t)p.esize, out_plane = (size_t)p.esize;
+  for (int i = 1; i < p.rank; ++i) { in_plane *= (size_t)p.in_dims[i]; out_plane *= (size_t)p.out_dims[i]; }
+  // whatever the caller queued on the compute stream before comes first
+  MB_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+  MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  MB_CUDA(c, cudaStreamWaitEvent(c->out_stream, c->ev_a, 0));
+  auto in_begin = [&](int j) { return D * j / nch; };
+  for (int j = 0; j < nch; ++j) {
+    const int64_t a = in_begin(j), b = in_begin(j + 1);
+    MB_CUDA(c, cudaMemcpyAsync((char *)d_in + a * in_plane, (const char *)host_in + a * in_plane, (size_t)(b - a) * in_plane,
+                               cudaMemcpyHostToDevice, c->comm_stream));
+    MB_CUDA(c, cudaEventRecord(c->pipe_events[j], c->comm_stream));
+  }
+  for (int k = 0; k < nch; ++k) {
+    const OuterRange r{OD * k / nch, OD * (k + 1) / nch};
+    // the last input plane this chunk reads (index repaired by Edge / Reflect / Continue stays within
+    // the stencil's reach of the array's ends; Wrap reaches the far end)
+    int64_t need_hi = r.o1 - 1 + p.shift[0] + p.max_off[0];
+    const int64_t need_lo = r.o0 + p.shift[0] + p.min_off[0];
+    if (need_hi > D - 1) need_hi = D - 1;
+    if (need_hi < 0) need_hi = 0;
+    int j_hi = 0;
+    while (j_hi + 1 < nch && in_begin(j_hi + 1) <= need_hi) ++j_hi;
+    const bool leaves = need_lo < 0 || r.o1 - 1 + p.shift[0] + p.max_off[0] > D - 1;
+    if (leaves && p.border != MB_FILL && p.border != MB_EDGE) {
+      // repaired indices: Wrap lands at the opposite end; Reflect / Continue within `reach` of this end
+      j_hi = p.border == MB_WRAP ? nch - 1 : std::max(j_hi, 0);
+      if (p.border != MB_WRAP) {
+        const int64_t far = std::min<int64_t>(D - 1, std::max<int64_t>(need_hi, reach + 1));
+        while (j_hi + 1 < nch && in_begin(j_hi + 1) <= far) ++j_hi;
+      }
+    }
+    MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_events[j_hi], 0));
+    int st = launch_plan(c, dp, d_in, d_out, &r);
+    if (st) return st;
+    MB_CUDA(c, cudaEventRecord(c->pipe_events[16 + k], c->stream));
+    MB_CUDA(c, cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
+    MB_CUDA(c, cudaMemcpyAsync((char *)host_out + r.o0 * out_plane, (const char *)d_out + r.o0 * out_plane,
+                               (size_t)(r.o1 - r.o0) * out_plane, cudaMemcpyDeviceToHost, c->out_stream));
+  }
+  (void)ob;
+  MB_CUDA(c, cudaStreamSynchronize(c->out_stream));
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -287,6 +353,8 @@ int mb_ctx_destroy(mb_ctx *h) {
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
+  for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   delete h;
@@ -309,6 +377,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   if (k == "force_generic") g.c->force_generic = (int)value;
   else if (k == "life_bitpack") g.c->life_bitpack = (int)value;
   else if (k == "tile_min_elems") g.c->tile_min_elems = value;
+  else if (k == "pipeline") g.c->pipeline = (int)value;
   else if (k == "no_tma") g.c->no_tma = (int)value;
   else if (k == "no_known") g.c->no_known = (int)value;
   else if (k == "tb2") g.c->tb2 = (int)value;
@@ -400,6 +469,7 @@ int mb_run(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *in_dims, const
   void *d_in = nullptr, *d_out = nullptr;
   if ((st = ensure_scratch(c, 0, ib ? ib : 1, &d_in))) return st;
   if ((st = ensure_scratch(c, 1, ob ? ob : 1, &d_out))) return st;
+  if ((st = run_pipelined(c, *dp, host_in, host_out, d_in, d_out)) != -1) return st;
   if ((st = copy_h2d(c, d_in, host_in, ib))) return st;
   if ((st = launch_plan(c, *dp, d_in, d_out, nullptr))) return st;
   if ((st = copy_d2h(c, host_out, d_out, ob))) return st;

@@ -69,7 +69,8 @@ struct ShardState;  // mb_shard.cu
 
 struct Ctx {
   int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, comm_stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, comm_stream = nullptr, out_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_events;  // host->host pipeline (mb_run): created on first use
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_a = nullptr, ev_b = nullptr;
   std::mutex mu;
   std::string err;
@@ -82,6 +83,7 @@ struct Ctx {
   int no_known = 0;        // mb_ctx_set_option("no_known"): skip the compile-time-coefficient kernels
   int tb2 = 1;             // mb_ctx_set_option("tb2"): fuse pairs of steps of iterated 3-D star stencils
   int64_t tile_min_elems = 16384;  // below this many output cells the generic kernel is used
+  int pipeline = 1;                // mb_run overlaps H2D / kernel / D2H over chunks of the outer dimension
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks
   void *scratch[3] = {nullptr, nullptr, nullptr};

@@ -1,0 +1,49 @@
+"""mb_run (host -> host) runs large single passes as a chunked H2D / kernel / D2H pipeline; the result
+must not depend on it.  Arrays here are just large enough to be split."""
+import numpy as np
+import pytest
+
+import massiv_b200 as M
+from helpers import bits_equal, border_obj
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BORDERS = ["fill", "wrap", "edge", "reflect", "continue"]
+
+
+@pytest.mark.parametrize("border", BORDERS)
+def test_conv2d_all_borders(border):
+    dev = M.Device.default()
+    rng = np.random.default_rng(11)
+    arr = rng.standard_normal((4100, 4099))
+    k = rng.standard_normal((5, 5))
+    st = M.makeConvolutionStencilFromKernel(k)
+    want = O.apply("conv", arr, size=(5, 5), coeffs=k.reshape(-1).tolist(), border=border, fill=0.5, nthreads=16)
+    got = M.compute(M.mapStencil(border_obj(border, 0.5), st, arr))
+    assert bits_equal(got, want)
+    dev.set_option("pipeline", 0)
+    try:
+        assert bits_equal(M.compute(M.mapStencil(border_obj(border, 0.5), st, arr)), want)
+    finally:
+        dev.set_option("pipeline", 1)
+
+
+def test_other_shapes():
+    rng = np.random.default_rng(12)
+    # 3-D star under Wrap (first and last chunks read the far end), asymmetric fold window, padding that grows the array
+    k = np.zeros((3, 3, 3))
+    k[1, 1, 1], k[0, 1, 1], k[2, 1, 1], k[1, 0, 1], k[1, 2, 1], k[1, 1, 0], k[1, 1, 2] = 0.4, .1, .1, .1, .1, .1, .1
+    vol = rng.random((140, 300, 310))
+    want = O.apply("conv", vol, size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border="wrap", nthreads=16)
+    assert bits_equal(M.compute(M.mapStencil(M.Wrap, M.makeConvolutionStencilFromKernel(k), vol)), want)
+    img = rng.integers(0, 255, size=(9000, 9001), dtype=np.uint8)
+    want = O.apply("max", img, size=(7, 3), border="continue", nthreads=16)
+    assert bits_equal(M.compute(M.mapStencil(M.Continue, M.maxStencil(M.Sz(7, 3)), img)), want)
+    arr = rng.standard_normal((4000, 4000))
+    want = O.apply("sum", arr, size=(3, 3), pad_lo=(5, 2), pad_hi=(6, 1), border="reflect", nthreads=16)
+    got = M.compute(M.applyStencil(M.Padding((5, 2), (6, 1), M.Reflect), M.sumStencil(M.Sz(3, 3)), arr))
+    assert bits_equal(got, want)
+    post = M.avgStencil(M.Sz(3, 3)).fmap("mul", 2.0).fmap("abs")
+    want = O.apply("avg", arr, size=(3, 3), border="edge", nthreads=16, post=[("mul", 2.0), ("abs",)])
+    assert bits_equal(M.compute(M.mapStencil(M.Edge, post, arr)), want)
