@@ -112,7 +112,9 @@ def oracle_spec(name):
 def stencil_spec(name, M):
     """(border, stencil[, second stencil]) in the product's host API"""
     if name == "heat3d":
-        return M.Fill(0.0), M.makeConvolutionStencilFromKernel(heat_kernel()).assumeFinite()
+        st = M.makeConvolutionStencilFromKernel(heat_kernel())
+        # MASSIV_B200_STRICT=1: no finite-input promise (every one of the 27 taps is evaluated)
+        return M.Fill(0.0), (st if os.environ.get("MASSIV_B200_STRICT") else st.assumeFinite())
     if name == "avg3x3":
         return M.Edge, M.avgStencil(M.Sz(3, 3))
     if name == "sobel":

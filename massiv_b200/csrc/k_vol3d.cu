@@ -61,10 +61,16 @@ template <typename T> __device__ __forceinline__ void lds_vec(T *dst, const T *s
   for (int v = 0; v < V; ++v) dst[v] = tmp[v];
 }
 
-template <typename T, int MODE, bool REV>
+// DETECT (STAR7 only): the kernel skips the 20 zero taps WITHOUT the caller's promise and reports through
+// `flag` whether any source value it read was Inf or NaN — the only inputs for which skipping a zero tap
+// changes the result (0 * Inf = NaN).  The dense kernel that follows on the stream takes `flag` as its
+// condition and returns at once when it is clear, so the strict result costs a star pass for finite data.
+template <typename T, int MODE, bool REV, bool DETECT>
 __global__ void __launch_bounds__(256, MODE == V3_STAR7 ? MB_V3_MINB : 1)
 vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const Coef27<T> K,
-             const T *__restrict__ in, T *__restrict__ out) {
+             const T *__restrict__ in, T *__restrict__ out, unsigned *flag) {
+  if (MODE == V3_DENSE27 && flag != nullptr && *reinterpret_cast<volatile unsigned *>(flag) == 0u) return;
+  unsigned bad = 0;
   using C = V3Cfg<T, MODE>;
   using A = Arith<T>;
   constexpr int V = C::V, R = C::R, S = C::S;
@@ -170,6 +176,10 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
         for (int r = 0; r < R; ++r) {
           lds_vec<T>(zm[r], s0 + r * C::BW);
           lds_vec<T>(zc[r], s1 + r * C::BW);
+          if (DETECT) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zm[r][v]) | nonfinite_bits(zc[r][v]);
+          }
         }
       }
 #pragma unroll 1
@@ -185,6 +195,10 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
           lds_vec<T>(zp[r], sn + r * C::BW);
           xl[r] = sm[r * C::BW - 1];
           xr[r] = sm[r * C::BW + V];
+          if (DETECT) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zp[r][v]);
+          }
         }
         const int gz = oz0 + j;
 #pragma unroll
@@ -311,10 +325,11 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
     }
     Lc += nz + 2;
   }
+  if (DETECT && bad) atomicOr(flag, 1u);
 }
 
-template <typename T, int MODE, bool REV>
-static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+template <typename T, int MODE, bool REV, bool DETECT = false>
+static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range, unsigned *flag = nullptr) {
   using C = V3Cfg<T, MODE>;
   const Plan &p = dp.p;
   V3Params P;
@@ -339,7 +354,7 @@ static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, c
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
   P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
-  auto kern = vol3d_kernel<T, MODE, REV>;
+  auto kern = vol3d_kernel<T, MODE, REV, DETECT>;
   static int occ_dev[64] = {0};
   int &occ = occ_dev[c->device & 63];
   if (occ == 0) {
@@ -367,7 +382,7 @@ static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, c
   }
   P.nitems = tiles * chunks;
   int grid = resident < P.nitems ? resident : P.nitems;
-  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out);
+  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out, flag);
   c->launches++;
   c->last_kernel = MODE == V3_STAR7 ? "vol3d_star7" : "vol3d_dense27";
   return check_cuda(c, cudaGetLastError(), "vol3d_kernel launch");
@@ -390,9 +405,62 @@ static int launch_v3_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const 
   // tile, which is aligned exactly when the window centre of output column 0 is (mapStencil: 0)
   if (p.shift[2] % (16 / (int)sizeof(T)) != 0) return -1;
   const bool rev = p.kind == MB_CONV;
-  const bool star = (p.flags & MB_FLAG_ASSUME_FINITE) && is_star<T>(p);
-  if (star) return rev ? launch_v3<T, V3_STAR7, true>(c, dp, i, o, r) : launch_v3<T, V3_STAR7, false>(c, dp, i, o, r);
+  const bool starshape = is_star<T>(p);
+  if (starshape && (p.flags & MB_FLAG_ASSUME_FINITE))
+    return rev ? launch_v3<T, V3_STAR7, true>(c, dp, i, o, r) : launch_v3<T, V3_STAR7, false>(c, dp, i, o, r);
+  // No promise: run the star kernel optimistically and let it report non-finite inputs; the strict
+  // 27-tap kernel follows on the stream and only does work when it has to.  Every source cell must pass
+  // through some thread's registers for the report to be complete: in-plane the cell grid has to be the
+  // array's own (along dim 0 every plane that is read is also loaded as a centre plane).
+  const bool inplane_same = p.shift[1] == 0 && p.shift[2] == 0 && p.out_dims[1] == p.in_dims[1] && p.out_dims[2] == p.in_dims[2];
+  bool fill_finite = true;  // a Fill element of Inf / NaN reaches the zero taps at the border
+  if (p.border == MB_FILL) {
+    T fv;
+    std::memcpy(&fv, p.fill, sizeof(T));
+    fill_finite = fv - fv == T(0);
+  }
+  if (starshape && inplane_same && fill_finite && !c->no_optimistic && ensure_flag(c) == MB_OK) {
+    MB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned), c->stream));
+    int st = rev ? launch_v3<T, V3_STAR7, true, true>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_STAR7, false, true>(c, dp, i, o, r, c->d_flag);
+    if (st) return st;
+    st = rev ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, r, c->d_flag);
+    c->last_kernel = "vol3d_star7";
+    return st;
+  }
   return rev ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, r) : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, r);
+}
+
+// the strict kernel, conditional on *cond (used by the optimistic two-step path)
+template <typename T>
+static int dense_cond_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const unsigned *cond) {
+  if (dp.p.shift[2] % (16 / (int)sizeof(T)) != 0) return -1;
+  return dp.p.kind == MB_CONV ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, nullptr, const_cast<unsigned *>(cond))
+                              : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, nullptr, const_cast<unsigned *>(cond));
+}
+int launch_vol3d_dense_cond(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const unsigned *cond) {
+  if (dp.p.elem == MB_F32) return dense_cond_t<float>(c, dp, d_in, d_out, cond);
+  if (dp.p.elem == MB_F64) return dense_cond_t<double>(c, dp, d_in, d_out, cond);
+  return -1;
+}
+
+__global__ void cond_copy_kernel(uint4 *dst, const uint4 *src, size_t n16, unsigned char *dst_tail, const unsigned char *src_tail,
+                                 int tail, const unsigned *cond) {
+  if (*reinterpret_cast<const volatile unsigned *>(cond) == 0u) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+int launch_cond_copy(Ctx *c, void *dst, const void *src, size_t bytes, const unsigned *cond) {
+  const size_t n16 = bytes / 16;
+  cond_copy_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((uint4 *)dst, (const uint4 *)src, n16, (unsigned char *)dst + n16 * 16,
+                                                         (const unsigned char *)src + n16 * 16, (int)(bytes - n16 * 16), cond);
+  c->launches++;
+  return check_cuda(c, cudaGetLastError(), "cond_copy_kernel launch");
+}
+
+int ensure_flag(Ctx *c) {
+  if (c->d_flag) return MB_OK;
+  if (cudaMalloc(&c->d_flag, 256) != cudaSuccess) { cudaGetLastError(); return MB_ERR_CUDA; }
+  return MB_OK;
 }
 
 int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {

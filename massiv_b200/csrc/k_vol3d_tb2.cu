@@ -103,9 +103,14 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
     }
 }
 
-template <typename T, bool REV, int R_>
+// DETECT: no finite-input promise.  The kernel reports through `flag` whether any source value or any
+// intermediate value (a finite input can overflow) was Inf or NaN; the caller then redoes the two steps
+// with the strict 27-tap kernel (conditional launches that return at once when the flag is clear).
+template <typename T, bool REV, int R_, bool DETECT>
 __global__ void __launch_bounds__(256, MB_TB2_MINB)
-vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out) {
+vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out,
+                 unsigned *flag) {
+  unsigned bad = 0;
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -188,6 +193,12 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     T Z0[R][V], Z1[R][V], Z2[R][V], U0[R][V], U1[R][V], U2[R][V];
     centres(Z0, Lc);
     centres(Z1, Lc + 1);
+    if (DETECT) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) bad |= nonfinite_bits(Z0[r][v]) | nonfinite_bits(Z1[r][v]);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -215,6 +226,12 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
       acquire(Lc + k + 2);
       centres(zp, Lc + k + 2);
+      if (DETECT) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zp[r][v]);
+      }
       // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
       star7<T, REV, R, V, BW>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * C::STAGE) + coff, zm, zc, zp, K, up);
       const bool in_z = ip + P.zoff >= 0 && ip + P.zoff < P.dglob;
@@ -226,6 +243,10 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (!(in_z && ((in_yx >> r) & 1u) && ((in_yx >> (8 + v)) & 1u))) up[r][v] = T(0);
+        if (DETECT) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) bad |= nonfinite_bits(up[r][v]);
+        }
         uint4 q;
         memcpy(&q, up[r], 16);
         *reinterpret_cast<uint4 *>(ub + r * BW) = q;
@@ -271,11 +292,12 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     }
     Lc += nz + 4;
   }
+  if (DETECT && bad) atomicOr(flag, 1u);
 }
 
-template <typename T, bool REV, int R_>
+template <typename T, bool REV, int R_, bool DETECT>
 static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
-                        int64_t dglob) {
+                        int64_t dglob, unsigned *flag) {
   using C = TB2Cfg<T, R_>;
   TB2Params P;
   std::memset(&P, 0, sizeof(P));
@@ -294,7 +316,7 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
   if (c->no_tma || !make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) return -1;
-  auto kern = vol3d_tb2_kernel<T, REV, R_>;
+  auto kern = vol3d_tb2_kernel<T, REV, R_, DETECT>;
   static int occ_dev[64] = {0};
   int &occ = occ_dev[c->device & 63];
   if (occ == 0) {
@@ -322,7 +344,7 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   }
   P.nitems = tiles * chunks;
   const int grid = resident < P.nitems ? resident : P.nitems;
-  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (T *)d_out);
+  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (T *)d_out, flag);
   c->launches++;
   c->last_kernel = "vol3d_tb2";
   return check_cuda(c, cudaGetLastError(), "vol3d_tb2_kernel launch");
@@ -356,10 +378,29 @@ bool tb2_desc_eligible(const mb_stencil_desc *d) {
 }
 
 // May two steps of this single-step plan be fused?  (the plan describes ONE application)
+// 1: yes, under the caller's finite promise; 2: yes, optimistically — the kernel checks what the promise
+// would have covered and the caller redoes the pair strictly when the check fails; 0: no.
+int vol3d_tb2_mode(Ctx *c, const Plan &p) {
+  if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return 0;
+  if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return 0;
+  if (p.border != MB_FILL) return 0;
+  for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) return 0;
+  for (int i = 0; i < 3; ++i)
+    if (p.size[i] != 3 || p.in_dims[i] < 1 || p.in_dims[i] >= (1ll << 30)) return 0;
+  if (p.shift[0] != 0 || p.shift[1] != 0 || p.shift[2] != 0) return 0;
+  for (int i = 0; i < 3; ++i) if (p.out_dims[i] != p.in_dims[i]) return 0;
+  if (p.out_elems < c->tile_min_elems) return 0;
+  const bool star = p.elem == MB_F32 ? star_only<float>(p) : (p.elem == MB_F64 ? star_only<double>(p) : false);
+  if (!star) return 0;
+  if (p.flags & MB_FLAG_ASSUME_FINITE) return 1;
+  return c->no_optimistic ? 0 : 2;
+}
+
+// the promise-only form: what the sharded loop (slabs with ghost planes) uses
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
+  if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
   if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return false;
   if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return false;
-  if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
   if (p.border != MB_FILL) return false;
   for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) return false;
   for (int i = 0; i < 3; ++i)
@@ -375,13 +416,16 @@ bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
 // handed in here; sz2 = 0: both applications are size-preserving along dim 0 (single GPU);
 // sz2 = 2: the buffer carries two ghost planes each side and in_dims[0] - 4 result planes come out.
 int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
-                     int64_t dglob) {
+                     int64_t dglob, unsigned *detect) {
   const bool rev = p.kind == MB_CONV;
-  if (p.elem == MB_F64)
-    return rev ? launch_tb2_r<double, true, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob)
-               : launch_tb2_r<double, false, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob);
-  return rev ? launch_tb2_r<float, true, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob)
-             : launch_tb2_r<float, false, MB_TB2_R>(c, p, d_in, d_out, range, sz2, zoff, dglob);
+#define MB_TB2_GO(T, REV, DET) launch_tb2_r<T, REV, MB_TB2_R, DET>(c, p, d_in, d_out, range, sz2, zoff, dglob, detect)
+  if (p.elem == MB_F64) {
+    if (detect) return rev ? MB_TB2_GO(double, true, true) : MB_TB2_GO(double, false, true);
+    return rev ? MB_TB2_GO(double, true, false) : MB_TB2_GO(double, false, false);
+  }
+  if (detect) return rev ? MB_TB2_GO(float, true, true) : MB_TB2_GO(float, false, true);
+  return rev ? MB_TB2_GO(float, true, false) : MB_TB2_GO(float, false, false);
+#undef MB_TB2_GO
 }
 
 }  // namespace mb

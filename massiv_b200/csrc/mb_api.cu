@@ -147,12 +147,26 @@ static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t
   }
   void *cur = a, *nxt = b;
   int64_t s = 0;
-  if (vol3d_tb2_applicable(c, dp->p) && dp->p.same_shape()) {
+  const int tb2 = dp->p.same_shape() ? vol3d_tb2_mode(c, dp->p) : 0;
+  if (tb2 == 2 && ensure_flag(c) != MB_OK) return fail(c, MB_ERR_CUDA, "cannot allocate the check flag");
+  if (tb2) {
     // temporal blocking: pairs of steps in one pass over HBM; an odd last step runs singly below
     for (; s + 2 <= n_steps; s += 2) {
-      st = launch_vol3d_tb2(c, dp->p, cur, nxt, nullptr, 0, 0, dp->p.in_dims[0]);
+      unsigned *flag = tb2 == 2 ? c->d_flag : nullptr;
+      if (flag) MB_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
+      st = launch_vol3d_tb2(c, dp->p, cur, nxt, nullptr, 0, 0, dp->p.in_dims[0], flag);
       if (st == -1) break;  // the array cannot be described to TMA: single steps
       if (st) return st;
+      if (flag) {
+        // no promise was given: if the kernel met Inf / NaN (in the input or the intermediate array) the
+        // pair is redone with the strict kernel — cur -> nxt -> cur, then copied to where the result
+        // belongs.  All three launches return immediately while the flag is clear.
+        if ((st = launch_vol3d_dense_cond(c, *dp, cur, nxt, flag)) == -1) return fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo");
+        if (st) return st;
+        if ((st = launch_vol3d_dense_cond(c, *dp, nxt, cur, flag))) return st;
+        if ((st = launch_cond_copy(c, nxt, cur, (size_t)dp->p.out_elems * dp->p.esize, flag))) return st;
+        c->last_kernel = "vol3d_tb2";
+      }
       void *t = cur; cur = nxt; nxt = t;
     }
   }
@@ -353,6 +367,7 @@ int mb_ctx_destroy(mb_ctx *h) {
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->d_flag) cudaFree(c->d_flag);
   for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
   if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -378,6 +393,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "life_bitpack") g.c->life_bitpack = (int)value;
   else if (k == "tile_min_elems") g.c->tile_min_elems = value;
   else if (k == "pipeline") g.c->pipeline = (int)value;
+  else if (k == "no_optimistic") g.c->no_optimistic = (int)value;
   else if (k == "no_tma") g.c->no_tma = (int)value;
   else if (k == "no_known") g.c->no_known = (int)value;
   else if (k == "tb2") g.c->tb2 = (int)value;

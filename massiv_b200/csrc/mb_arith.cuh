@@ -63,6 +63,12 @@ template <> struct Arith<int32_t> : IntArith<int32_t, uint32_t> {};
 template <> struct Arith<uint64_t> : IntArith<uint64_t, uint64_t> {};
 template <> struct Arith<int64_t> : IntArith<int64_t, uint64_t> {};
 
+// Inf or NaN?  (exponent field all ones) — integer pipe only, for the optimistic star kernels
+__device__ __forceinline__ unsigned nonfinite_bits(float x) { return (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u; }
+__device__ __forceinline__ unsigned nonfinite_bits(double x) {
+  return ((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u;
+}
+
 // Correctly rounded x / n for a small positive integer n (avgStencil's `/ fromIntegral n`,
 // Array/Stencil.hs:479-481) in three operations instead of the ~15-instruction IEEE divide:
 //     q = RN(x * y), y = RN(1/n);   r = x - n*q  (exact in one FMA);   q' = RN(q + r*y)

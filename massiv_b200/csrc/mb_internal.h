@@ -83,9 +83,11 @@ struct Ctx {
   int no_known = 0;        // mb_ctx_set_option("no_known"): skip the compile-time-coefficient kernels
   int tb2 = 1;             // mb_ctx_set_option("tb2"): fuse pairs of steps of iterated 3-D star stencils
   int64_t tile_min_elems = 16384;  // below this many output cells the generic kernel is used
+  int no_optimistic = 0;           // 1: never skip zero taps without the caller's promise (always the 27-tap kernel)
   int pipeline = 1;                // mb_run overlaps H2D / kernel / D2H over chunks of the outer dimension
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks
+  unsigned *d_flag = nullptr;  // "the optimistic kernel met a non-finite value": set by it, read by the conditional redo
   void *scratch[3] = {nullptr, nullptr, nullptr};
   size_t scratch_bytes[3] = {0, 0, 0};
   void *pinned = nullptr;
@@ -122,6 +124,13 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
 int launch_linescan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
 int launch_direct2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
 int launch_post(Ctx *c, const Plan &p, void *d_out, const OuterRange *range);  // in-place post-maps over the output
+int ensure_flag(Ctx *c);  // allocates c->d_flag
+// strict 27-tap step that runs only when *cond != 0 (nullptr: always)
+int launch_vol3d_dense_cond(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const unsigned *cond);
+// dst <- src when *cond != 0
+int launch_cond_copy(Ctx *c, void *dst, const void *src, size_t bytes, const unsigned *cond);
+// 0: two-step passes not possible; 1: under the caller's finite promise; 2: optimistic (checked) — see k_vol3d_tb2.cu
+int vol3d_tb2_mode(Ctx *c, const Plan &p);
 int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
@@ -132,7 +141,7 @@ int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_step
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p);
 bool tb2_desc_eligible(const mb_stencil_desc *d);  // host-only: could this descriptor ever take the fused path?
 int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
-                     int64_t dglob);
+                     int64_t dglob, unsigned *detect = nullptr);
 
 void shard_destroy(Ctx *c);
 int shard_plan(const mb_stencil_desc *d, const int64_t *global_dims, int n_ranks, int rank, mb_shard_plan *out,
