@@ -62,10 +62,13 @@ template <typename T> __device__ __forceinline__ void lds_vec(T *dst, const T *s
 }
 
 // DETECT (STAR7 only): the kernel skips the 20 zero taps WITHOUT the caller's promise and reports through
-// `flag` whether any source value it read was Inf or NaN — the only inputs for which skipping a zero tap
-// changes the result (0 * Inf = NaN).  The dense kernel that follows on the stream takes `flag` as its
-// condition and returns at once when it is clear, so the strict result costs a star pass for finite data.
-template <typename T, int MODE, bool REV, bool DETECT>
+// `flag` whether an Inf or NaN was involved — the only inputs for which skipping a zero tap changes the
+// result (0 * Inf = NaN).  DETECT 2 inspects every source value that passes through registers.  DETECT 1
+// (centre coefficient non-zero) inspects the RESULTS instead, half the work: a non-finite source cell
+// makes the result at its own position non-finite through the centre tap (Inf * k, NaN * k; nothing
+// added to it brings it back).  The dense kernel that follows on the stream takes `flag` as its condition
+// and returns at once when it is clear, so the strict result costs a star pass for finite data.
+template <typename T, int MODE, bool REV, int DETECT>
 __global__ void __launch_bounds__(256, MODE == V3_STAR7 ? MB_V3_MINB : 1)
 vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const Coef27<T> K,
              const T *__restrict__ in, T *__restrict__ out, unsigned *flag) {
@@ -176,9 +179,9 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
         for (int r = 0; r < R; ++r) {
           lds_vec<T>(zm[r], s0 + r * C::BW);
           lds_vec<T>(zc[r], s1 + r * C::BW);
-          if (DETECT) {
+          if (DETECT) {  // the plane below the item's first result plane is nobody's result in this launch
 #pragma unroll
-            for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zm[r][v]) | nonfinite_bits(zc[r][v]);
+            for (int v = 0; v < V; ++v) { track_magnitude(bad, zm[r][v]); if (DETECT == 2) track_magnitude(bad, zc[r][v]); }
           }
         }
       }
@@ -195,9 +198,9 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
           lds_vec<T>(zp[r], sn + r * C::BW);
           xl[r] = sm[r * C::BW - 1];
           xr[r] = sm[r * C::BW + V];
-          if (DETECT) {
+          if (DETECT == 2 || (DETECT == 1 && j == nz - 1)) {  // ... and neither is the plane above its last one
 #pragma unroll
-            for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zp[r][v]);
+            for (int v = 0; v < V; ++v) track_magnitude(bad, zp[r][v]);
           }
         }
         const int gz = oz0 + j;
@@ -221,6 +224,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
             acc = A::add(A::mul(REV ? up : dn, K.k[16]), acc);
             acc = A::add(A::mul(REV ? zm[r][v] : zp[r][v], K.k[22]), acc);
             res[v] = acc;
+            if (DETECT == 1) track_magnitude(bad, acc);
           }
           const int gy = oy0 + ly + r, gx = ox0 + lx;
           if (gy < P.out_h && gx < P.out_w) {
@@ -325,10 +329,10 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
     }
     Lc += nz + 2;
   }
-  if (DETECT && bad) atomicOr(flag, 1u);
+  if (DETECT && magnitude_nonfinite<T>(bad)) atomicOr(flag, 1u);
 }
 
-template <typename T, int MODE, bool REV, bool DETECT = false>
+template <typename T, int MODE, bool REV, int DETECT = 0>
 static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range, unsigned *flag = nullptr) {
   using C = V3Cfg<T, MODE>;
   const Plan &p = dp.p;
@@ -421,7 +425,12 @@ static int launch_v3_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const 
   }
   if (starshape && inplane_same && fill_finite && !c->no_optimistic && ensure_flag(c) == MB_OK) {
     MB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned), c->stream));
-    int st = rev ? launch_v3<T, V3_STAR7, true, true>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_STAR7, false, true>(c, dp, i, o, r, c->d_flag);
+    const T centre = reinterpret_cast<const T *>(p.c1.data())[13];
+    int st;
+    if (centre != T(0))  // (a NaN centre makes every result NaN: the check fires, the redo agrees)
+      st = rev ? launch_v3<T, V3_STAR7, true, 1>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_STAR7, false, 1>(c, dp, i, o, r, c->d_flag);
+    else
+      st = rev ? launch_v3<T, V3_STAR7, true, 2>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_STAR7, false, 2>(c, dp, i, o, r, c->d_flag);
     if (st) return st;
     st = rev ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, r, c->d_flag);
     c->last_kernel = "vol3d_star7";

@@ -103,10 +103,13 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
     }
 }
 
-// DETECT: no finite-input promise.  The kernel reports through `flag` whether any source value or any
-// intermediate value (a finite input can overflow) was Inf or NaN; the caller then redoes the two steps
-// with the strict 27-tap kernel (conditional launches that return at once when the flag is clear).
-template <typename T, bool REV, int R_, bool DETECT>
+// DETECT: no finite-input promise.  The kernel reports through `flag` whether an Inf or NaN was involved
+// — in the source or in the intermediate array (a finite input can overflow); the caller then redoes the
+// two steps with the strict 27-tap kernel (conditional launches that return at once when the flag is
+// clear).  DETECT 2 inspects every source and intermediate value.  DETECT 1 (centre coefficient non-zero)
+// inspects the RESULTS only: a non-finite value at a cell makes the next application's value at the same
+// cell non-finite through the centre tap, so it always surfaces in the result tile that owns the cell.
+template <typename T, bool REV, int R_, int DETECT>
 __global__ void __launch_bounds__(256, MB_TB2_MINB)
 vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out,
                  unsigned *flag) {
@@ -193,11 +196,11 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     T Z0[R][V], Z1[R][V], Z2[R][V], U0[R][V], U1[R][V], U2[R][V];
     centres(Z0, Lc);
     centres(Z1, Lc + 1);
-    if (DETECT) {
+    if (DETECT == 2) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int v = 0; v < V; ++v) bad |= nonfinite_bits(Z0[r][v]) | nonfinite_bits(Z1[r][v]);
+        for (int v = 0; v < V; ++v) { track_magnitude(bad, Z0[r][v]); track_magnitude(bad, Z1[r][v]); }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -226,11 +229,11 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
       acquire(Lc + k + 2);
       centres(zp, Lc + k + 2);
-      if (DETECT) {
+      if (DETECT == 2) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int v = 0; v < V; ++v) bad |= nonfinite_bits(zp[r][v]);
+          for (int v = 0; v < V; ++v) track_magnitude(bad, zp[r][v]);
       }
       // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
       star7<T, REV, R, V, BW>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * C::STAGE) + coff, zm, zc, zp, K, up);
@@ -243,9 +246,9 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (!(in_z && ((in_yx >> r) & 1u) && ((in_yx >> (8 + v)) & 1u))) up[r][v] = T(0);
-        if (DETECT) {
+        if (DETECT == 2) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) bad |= nonfinite_bits(up[r][v]);
+          for (int v = 0; v < V; ++v) track_magnitude(bad, up[r][v]);
         }
         uint4 q;
         memcpy(&q, up[r], 16);
@@ -262,6 +265,10 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if ((rows >> r) & 1u) {
+            if (DETECT == 1) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) track_magnitude(bad, res[r][v]);
+            }
             if (whole) {
               uint4 q;
               memcpy(&q, res[r], 16);
@@ -292,10 +299,10 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     }
     Lc += nz + 4;
   }
-  if (DETECT && bad) atomicOr(flag, 1u);
+  if (DETECT && magnitude_nonfinite<T>(bad)) atomicOr(flag, 1u);
 }
 
-template <typename T, bool REV, int R_, bool DETECT>
+template <typename T, bool REV, int R_, int DETECT>
 static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
                         int64_t dglob, unsigned *flag) {
   using C = TB2Cfg<T, R_>;
@@ -420,11 +427,15 @@ int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const
   const bool rev = p.kind == MB_CONV;
 #define MB_TB2_GO(T, REV, DET) launch_tb2_r<T, REV, MB_TB2_R, DET>(c, p, d_in, d_out, range, sz2, zoff, dglob, detect)
   if (p.elem == MB_F64) {
-    if (detect) return rev ? MB_TB2_GO(double, true, true) : MB_TB2_GO(double, false, true);
-    return rev ? MB_TB2_GO(double, true, false) : MB_TB2_GO(double, false, false);
+    const bool centre = reinterpret_cast<const double *>(p.c1.data())[13] != 0.0;
+    if (detect && centre) return rev ? MB_TB2_GO(double, true, 1) : MB_TB2_GO(double, false, 1);
+    if (detect) return rev ? MB_TB2_GO(double, true, 2) : MB_TB2_GO(double, false, 2);
+    return rev ? MB_TB2_GO(double, true, 0) : MB_TB2_GO(double, false, 0);
   }
-  if (detect) return rev ? MB_TB2_GO(float, true, true) : MB_TB2_GO(float, false, true);
-  return rev ? MB_TB2_GO(float, true, false) : MB_TB2_GO(float, false, false);
+  const bool centre = reinterpret_cast<const float *>(p.c1.data())[13] != 0.0f;
+  if (detect && centre) return rev ? MB_TB2_GO(float, true, 1) : MB_TB2_GO(float, false, 1);
+  if (detect) return rev ? MB_TB2_GO(float, true, 2) : MB_TB2_GO(float, false, 2);
+  return rev ? MB_TB2_GO(float, true, 0) : MB_TB2_GO(float, false, 0);
 #undef MB_TB2_GO
 }
 

@@ -63,6 +63,14 @@ template <> struct Arith<int32_t> : IntArith<int32_t, uint32_t> {};
 template <> struct Arith<uint64_t> : IntArith<uint64_t, uint64_t> {};
 template <> struct Arith<int64_t> : IntArith<int64_t, uint64_t> {};
 
+// Running maximum of |x|'s high word: two integer instructions per value; Inf or NaN was seen iff the
+// maximum reaches the all-ones exponent
+__device__ __forceinline__ void track_magnitude(unsigned &m, float x) { m = max(m, __float_as_uint(x) & 0x7fffffffu); }
+__device__ __forceinline__ void track_magnitude(unsigned &m, double x) { m = max(m, (unsigned)__double2hiint(x) & 0x7fffffffu); }
+template <typename T> __device__ __forceinline__ bool magnitude_nonfinite(unsigned m) {
+  return m >= (sizeof(T) == 4 ? 0x7f800000u : 0x7ff00000u);
+}
+
 // Inf or NaN?  (exponent field all ones) — integer pipe only, for the optimistic star kernels
 __device__ __forceinline__ unsigned nonfinite_bits(float x) { return (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u; }
 __device__ __forceinline__ unsigned nonfinite_bits(double x) {

@@ -98,3 +98,19 @@ def test_cases_that_stay_strict(dev):
     got = M.compute(M.applyStencil(M.noPadding, st, dev.fromHost(a))).toHost()
     assert dev.last_kernel != "vol3d_star7"
     assert bits_equal(got, O.apply("conv", a, size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), pad_lo=(0, 0, 0), pad_hi=(0, 0, 0)))
+
+
+def test_chunked_and_ranged_launches_see_their_halo_planes():
+    """mb_run splits large host->host passes into chunks of output planes: a non-finite value in the plane
+    just outside a chunk must still be noticed by that chunk's launch"""
+    dev = M.Device.default()
+    rng = np.random.default_rng(21)
+    k = heat()
+    a = rng.random((96, 520, 530))   # ~212 MB in + out: two or more chunks
+    kw = dict(size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border="fill", fill=0.0)
+    st = M.makeConvolutionStencilFromKernel(k)
+    for z in (47, 48, 49, 0, 95, 23, 24, 71, 72):
+        a2 = a.copy()
+        a2[z, 100, 200] = np.inf
+        want = O.apply("conv", a2, nthreads=16, **kw)
+        assert bits_equal(M.compute(M.mapStencil(M.Fill(0.0), st, a2)), want), z
