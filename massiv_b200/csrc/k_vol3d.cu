@@ -466,6 +466,17 @@ int launch_cond_copy(Ctx *c, void *dst, const void *src, size_t bytes, const uns
   return check_cuda(c, cudaGetLastError(), "cond_copy_kernel launch");
 }
 
+__global__ void cond_fill_kernel(unsigned char *dst, size_t n_elems, int esize, unsigned long long bits, const unsigned *cond) {
+  if (*reinterpret_cast<const volatile unsigned *>(cond) == 0u) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_elems; i += (size_t)gridDim.x * blockDim.x)
+    for (int b = 0; b < esize; ++b) dst[i * esize + b] = (unsigned char)(bits >> (8 * b));
+}
+int launch_cond_fill(Ctx *c, void *dst, size_t n_elems, int esize, unsigned long long bits, const unsigned *cond) {
+  cond_fill_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>((unsigned char *)dst, n_elems, esize, bits, cond);
+  c->launches++;
+  return check_cuda(c, cudaGetLastError(), "cond_fill_kernel launch");
+}
+
 int ensure_flag(Ctx *c) {
   if (c->d_flag) return MB_OK;
   if (cudaMalloc(&c->d_flag, 256) != cudaSuccess) { cudaGetLastError(); return MB_ERR_CUDA; }

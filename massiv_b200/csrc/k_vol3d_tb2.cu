@@ -196,7 +196,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     T Z0[R][V], Z1[R][V], Z2[R][V], U0[R][V], U1[R][V], U2[R][V];
     centres(Z0, Lc);
     centres(Z1, Lc + 1);
-    if (DETECT == 2) {
+    if (DETECT) {  // the two planes below the item's first result plane are nobody's result in this launch
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -229,7 +229,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
       acquire(Lc + k + 2);
       centres(zp, Lc + k + 2);
-      if (DETECT == 2) {
+      if (DETECT == 2 || (DETECT == 1 && k >= nz)) {  // ... nor are the two planes above its last one
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -246,7 +246,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (!(in_z && ((in_yx >> r) & 1u) && ((in_yx >> (8 + v)) & 1u))) up[r][v] = T(0);
-        if (DETECT == 2) {
+        if (DETECT == 2 || (DETECT == 1 && (k == 0 || k == nz + 1))) {  // intermediate planes outside the result range
 #pragma unroll
           for (int v = 0; v < V; ++v) track_magnitude(bad, up[r][v]);
         }
@@ -371,7 +371,7 @@ static bool star_only(const Plan &p) {
 // descriptor-only eligibility (decides how many ghost planes a sharded slab carries)
 bool tb2_desc_eligible(const mb_stencil_desc *d) {
   if (!d || d->rank != 3 || (d->kind != MB_CONV && d->kind != MB_CORR) || !d->coeffs || d->n_post) return false;
-  if (!(d->flags & MB_FLAG_ASSUME_FINITE) || d->border != MB_FILL) return false;
+  if (d->border != MB_FILL) return false;  // (with or without the finite promise: the checked form covers the rest)
   if (d->elem != MB_F32 && d->elem != MB_F64) return false;
   const int es = d->elem == MB_F32 ? 4 : 8;
   for (int i = 0; i < es; ++i) if (d->fill[i] != 0) return false;
@@ -403,9 +403,18 @@ int vol3d_tb2_mode(Ctx *c, const Plan &p) {
   return c->no_optimistic ? 0 : 2;
 }
 
-// the promise-only form: what the sharded loop (slabs with ghost planes) uses
+// the form the sharded loop (slabs with ghost planes) uses: 0 / 1 (promise) / 2 (checked), as above
+int vol3d_tb2_slab_mode(Ctx *c, const Plan &p) {
+  Plan q = p;
+  q.flags |= MB_FLAG_ASSUME_FINITE;
+  if (!vol3d_tb2_applicable(c, q)) return 0;
+  if (p.flags & MB_FLAG_ASSUME_FINITE) return 1;
+  return c->no_optimistic ? 0 : 2;
+}
+
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
   if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
+  if ((p.in_dims[2] * p.esize) % 16 != 0) return false;  // TMA: row pitch in whole 16-byte units
   if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return false;
   if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return false;
   if (p.border != MB_FILL) return false;

@@ -139,6 +139,8 @@ int launch_life(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out);
 int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_steps, void **result);
 // 3-D star stencils, two steps per pass (k_vol3d_tb2.cu)
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p);
+int vol3d_tb2_slab_mode(Ctx *c, const Plan &p);
+int launch_cond_fill(Ctx *c, void *dst, size_t n_elems, int esize, unsigned long long bits, const unsigned *cond);
 bool tb2_desc_eligible(const mb_stencil_desc *d);  // host-only: could this descriptor ever take the fused path?
 int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const OuterRange *range, int sz2, int64_t zoff,
                      int64_t dglob, unsigned *detect = nullptr);

@@ -610,11 +610,12 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
   std::shared_ptr<DevPlan> dp, dp2;
   if ((st = get_dev_plan(c, &ld, in_dims, &dp))) return st;
   if (dp->p.out_dims[0] != sp.local_planes) return fail(c, MB_ERR_SIZE_MISMATCH, "internal: slab geometry");
-  bool use_tb2 = false;
+  int tb2_mode = 0;  // 1: fused pairs under the caller's finite promise; 2: fused pairs, checked (k_vol3d_tb2.cu)
   if (extra_lo > 0 && extra_lo == sp.step_halo_lo && extra_hi == sp.step_halo_hi && sp.halo_lo == 2 && sp.halo_hi == 2) {
     in_dims[0] = sp.halo_lo + sp.local_planes + sp.halo_hi;
     if ((st = get_dev_plan(c, &ld, in_dims, &dp2))) return st;
-    use_tb2 = vol3d_tb2_applicable(c, dp2->p);
+    tb2_mode = vol3d_tb2_slab_mode(c, dp2->p);
+    if (tb2_mode == 2 && ensure_flag(c) != MB_OK) tb2_mode = 0;
   }
 
   SlabGeom g;
@@ -664,7 +665,8 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
                      getenv("MASSIV_B200_FORCE_SPLIT") != nullptr;  // experiment knob: peel boundary planes even when alone
   int cur = 0;
   for (int64_t s = 0; s < n_steps;) {
-    const bool two = use_tb2 && n_steps - s >= 2;  // a fused pair of steps, or one step
+    const bool two = tb2_mode && n_steps - s >= 2;  // a fused pair of steps, or one step
+    const bool checked = two && tb2_mode == 2;       // no finite promise: nothing may leave before the check
     const int64_t adv = two ? 2 : 1;
     char *in = bufs[cur], *out_base = bufs[1 - cur];
     char *out = out_base + (size_t)g.lo * g.plane_bytes;  // the rank's own planes start after the lower ghost
@@ -672,17 +674,41 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
     ++k;  // this round's number (the same on every rank)
     auto launch = [&](const OuterRange &r) -> int {
       if (r.o1 <= r.o0) return MB_OK;
-      if (two) return launch_vol3d_tb2(c, dp2->p, in, out, &r, (int)g.lo, sp.first_plane - g.lo, global_dims[0]);
+      if (two && !checked) return launch_vol3d_tb2(c, dp2->p, in, out, &r, (int)g.lo, sp.first_plane - g.lo, global_dims[0]);
+      if (two) {
+        // optimistic pair over the whole slab; if the kernel met Inf / NaN the pair is redone with the strict
+        // kernel: in -> (intermediate, parked in the out buffer one plane up) -> own planes of in -> out.
+        // The four follow-up launches return at once while the flag is clear.
+        MB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned), c->stream));
+        int e = launch_vol3d_tb2(c, dp2->p, in, out, &r, (int)g.lo, sp.first_plane - g.lo, global_dims[0], c->d_flag);
+        if (e) return e;
+        char *mid = out_base + g.plane_bytes;  // intermediate planes -1 .. local of the slab
+        if ((e = launch_vol3d_dense_cond(c, *dp2, in, mid, c->d_flag))) return e == -1 ? fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo") : e;
+        const size_t plane_elems = g.plane_bytes / dp->p.esize;
+        if (sp.first_plane - 1 < 0)  // the border applies to the intermediate array: Fill outside the global array
+          if ((e = launch_cond_fill(c, mid, plane_elems, dp->p.esize, 0ull, c->d_flag))) return e;
+        if (sp.first_plane + g.local >= global_dims[0])
+          if ((e = launch_cond_fill(c, mid + (size_t)(g.local + 1) * g.plane_bytes, plane_elems, dp->p.esize, 0ull, c->d_flag))) return e;
+        char *own_in = in + (size_t)g.lo * g.plane_bytes;
+        if ((e = launch_vol3d_dense_cond(c, *dp, mid, own_in, c->d_flag))) return e == -1 ? fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo") : e;
+        if ((e = launch_cond_copy(c, out, own_in, (size_t)g.local * g.plane_bytes, c->d_flag))) return e;
+        c->last_kernel = "vol3d_tb2";
+        return MB_OK;
+      }
       return launch_plan(c, *dp, in + (size_t)extra_lo * g.plane_bytes, out, &r);
     };
     if (pp.on && (st = recv_ghosts_p2p(c, sp, g, pp, bufs, cur, k))) return st;  // the neighbours' planes for this round
     // 1. the planes the neighbours are waiting for (a full ghost depth at either end) first
     int64_t top_end = g.hi < g.local ? g.hi : g.local;                        // result planes [0, top_end)
     int64_t bot_begin = g.local - g.lo > top_end ? g.local - g.lo : top_end;  // result planes [bot_begin, local)
-    if (last || !talks) { top_end = 0; bot_begin = g.local; }  // nobody waits: one launch
+    if (last || !talks || checked) { top_end = 0; bot_begin = g.local; }  // nobody waits / may not be served yet: one launch
     const OuterRange r1{0, top_end}, r2{bot_begin, g.local}, r3{top_end, bot_begin};
-    if ((st = launch(r1))) return st;
-    if ((st = launch(r2))) return st;
+    if (checked) {
+      if ((st = launch(r3))) return st;
+    } else {
+      if ((st = launch(r1))) return st;
+      if ((st = launch(r2))) return st;
+    }
     if (!last) {
       if (pp.on) {
         // 2. copy engines push the new boundary planes into the neighbours' staging slots of that parity;
@@ -697,7 +723,7 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
       }
     }
     // 3. the interior
-    if ((st = launch(r3))) return st;
+    if (!checked && (st = launch(r3))) return st;
     if (!last) {
       // physical-border ghosts that are copies of own planes (Edge / Reflect / Continue / 1-rank Wrap)
       if ((st = fill_local_ghosts(c, sp, g, out_base, *dp, false, c->stream))) return st;

@@ -31,6 +31,11 @@ def main():
               rng.random((16 * world, 48, 128)).astype(np.float32), 4),
              ("heat strict", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), rng.random((16 * world, 33, 65)), 4),
              ("heat strict inf", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), "inf", 4),
+             ("strict fused", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), rng.random((24 * world + 2, 64, 128)), 6),
+             ("strict fused inf", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), "inf128", 5),
+             ("strict ghost hi", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), "one@16", 4),
+             ("strict ghost lo", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), "one@15", 4),
+             ("strict ghost far", M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), "one@17", 2),
              ("heat wrap", M.Wrap, M.makeConvolutionStencilFromKernel(k).assumeFinite(), rng.random((20 * world, 32, 64)), 5),
              ("heat reflect", M.Reflect, M.makeConvolutionStencilFromKernel(rng.standard_normal((3, 3, 3))), rng.random((12 * world, 32, 64)), 3),
              ("avg2d edge", M.Edge, M.avgStencil(M.Sz(3, 3)), rng.random((64 * world + 5, 256)), 6),
@@ -38,9 +43,13 @@ def main():
     ok = True
     for name, border, st, arr, n in cases:
         if isinstance(arr, str):  # non-finite values on and next to the slab boundaries, no finite promise
-            arr = rng.random((16 * world, 33, 65))
-            for r in range(world):
-                arr[16 * r, 5 + r, 7], arr[16 * r + 15, 20, 40 + r], arr[16 * r + 8, 0, 0] = np.inf, np.nan, -np.inf
+            arr_spec = arr
+            arr = rng.random((16 * world, 33, 65) if arr == "inf" else (16 * world, 64, 128))
+            if arr_spec.startswith("one@"):   # a single value that one rank owns and its neighbour only sees as a ghost
+                arr[int(arr_spec[4:]), 10, 10] = np.inf
+            else:
+                for r in range(world):
+                    arr[16 * r, 5 + r, 7], arr[16 * r + 15, 20, 40 + r], arr[16 * r + 8, 0, 0] = np.inf, np.nan, -np.inf
         desc = M.mapStencil(border, st, arr).desc()
         sp = sharding.shard_plan(desc, arr.shape, world, rank)
         mine = np.ascontiguousarray(arr[sp.first_plane:sp.first_plane + sp.local_planes])

@@ -131,6 +131,7 @@ def test_single_rank_hostcheck_covers_every_border():
 
 def test_shard_plan_partition_and_ghost_sources():
     k = np.zeros((3, 3, 3))
+    k[0, 0, 0] = 1.0   # a corner tap: not star-shaped, so one step per round
     arr = np.zeros((10, 4, 4))
     st = M.makeConvolutionStencilFromKernel(k)
     # Fill: physical borders are constant planes, inner boundaries come from the neighbours
@@ -162,14 +163,15 @@ def test_shard_plan_partition_and_ghost_sources():
     p1 = sharding.shard_plan(d, arr.shape, 2, 1)
     assert (p.recv_upper_from, p.send_first_to, p.send_last_to, p.recv_lower_from) == (1, -1, -1, -1)
     assert (p1.recv_upper_from, p1.send_first_to, p1.send_last_to, p1.recv_lower_from) == (-1, 0, -1, -1)
-    # a star-shaped kernel with the finite promise under Fill 0 is iterated two steps per pass: the slab
-    # carries two ghost planes each side although one step reads one
+    # a star-shaped kernel under Fill 0 is iterated two steps per pass (with or without the finite promise):
+    # the slab carries two ghost planes each side although one step reads one
     ks = np.zeros((3, 3, 3))
     ks[1, 1, 1], ks[0, 1, 1], ks[2, 1, 1] = 0.4, 0.1, 0.1
     ds = M.mapStencil(M.Fill(0.0), M.makeConvolutionStencilFromKernel(ks).assumeFinite(), arr).desc()
     ps = sharding.shard_plan(ds, arr.shape, 2, 0)
     assert (ps.halo_lo, ps.halo_hi, ps.step_halo_lo, ps.step_halo_hi) == (2, 2, 1, 1)
     assert list(ps.ghost_lo_src)[:2] == [_abi.GHOST_FILL] * 2 and list(ps.ghost_hi_src)[:2] == [_abi.GHOST_REMOTE] * 2
+    assert sharding.shard_plan(M.mapStencil(M.Fill(0.0), M.makeConvolutionStencilFromKernel(ks), arr).desc(), arr.shape, 2, 0).halo_lo == 2
     assert sharding.shard_plan(M.mapStencil(M.Fill(1.0), M.makeConvolutionStencilFromKernel(ks).assumeFinite(), arr).desc(),
                                arr.shape, 2, 0).halo_lo == 1   # non-zero Fill: single steps
     # slabs thinner than the halo are refused, as is a shape-changing stencil
