@@ -161,6 +161,9 @@ int mb_sync(mb_ctx *ctx);
 int mb_ctx_set_option(mb_ctx *ctx, const char *key, int64_t value);
 /* number of kernels of THIS library launched through the context so far */
 int64_t mb_launch_count(mb_ctx *ctx);
+/* of those, the helper launches: conditional follow-ups of the checked kernels (they return at once
+ * unless a check failed), post-map passes, constant ghost-plane fills */
+int64_t mb_aux_launch_count(mb_ctx *ctx);
 /* name of the kernel family the last launch used ("generic", "tile2d", ...); for tests/bench */
 const char *mb_last_kernel(mb_ctx *ctx);
 

@@ -74,6 +74,7 @@ static int launch_post_t(Ctx *c, const PostParams &P, void *data, size_t n) {
   if (blocks > cap) blocks = cap;
   post_kernel<T><<<(unsigned)blocks, 256, 0, c->stream>>>(P, (T *)data, n);
   c->launches++;
+  c->aux_launches++;
   return check_cuda(c, cudaGetLastError(), "post_kernel launch");
 }
 

@@ -433,6 +433,7 @@ static int launch_v3_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const 
       st = rev ? launch_v3<T, V3_STAR7, true, 2>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_STAR7, false, 2>(c, dp, i, o, r, c->d_flag);
     if (st) return st;
     st = rev ? launch_v3<T, V3_DENSE27, true>(c, dp, i, o, r, c->d_flag) : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, r, c->d_flag);
+    c->aux_launches++;
     c->last_kernel = "vol3d_star7";
     return st;
   }
@@ -447,6 +448,7 @@ static int dense_cond_t(Ctx *c, const DevPlan &dp, const void *i, void *o, const
                               : launch_v3<T, V3_DENSE27, false>(c, dp, i, o, nullptr, const_cast<unsigned *>(cond));
 }
 int launch_vol3d_dense_cond(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const unsigned *cond) {
+  if (cond) c->aux_launches++;
   if (dp.p.elem == MB_F32) return dense_cond_t<float>(c, dp, d_in, d_out, cond);
   if (dp.p.elem == MB_F64) return dense_cond_t<double>(c, dp, d_in, d_out, cond);
   return -1;
@@ -463,6 +465,7 @@ int launch_cond_copy(Ctx *c, void *dst, const void *src, size_t bytes, const uns
   cond_copy_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((uint4 *)dst, (const uint4 *)src, n16, (unsigned char *)dst + n16 * 16,
                                                          (const unsigned char *)src + n16 * 16, (int)(bytes - n16 * 16), cond);
   c->launches++;
+  c->aux_launches++;
   return check_cuda(c, cudaGetLastError(), "cond_copy_kernel launch");
 }
 
@@ -474,6 +477,7 @@ __global__ void cond_fill_kernel(unsigned char *dst, size_t n_elems, int esize, 
 int launch_cond_fill(Ctx *c, void *dst, size_t n_elems, int esize, unsigned long long bits, const unsigned *cond) {
   cond_fill_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>((unsigned char *)dst, n_elems, esize, bits, cond);
   c->launches++;
+  c->aux_launches++;
   return check_cuda(c, cudaGetLastError(), "cond_fill_kernel launch");
 }
 

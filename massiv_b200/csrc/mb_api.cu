@@ -410,6 +410,7 @@ int mb_sync(mb_ctx *h) {
 }
 
 int64_t mb_launch_count(mb_ctx *h) { return h ? h->c.launches : 0; }
+int64_t mb_aux_launch_count(mb_ctx *h) { return h ? h->c.aux_launches : 0; }
 const char *mb_last_kernel(mb_ctx *h) { return h ? h->c.last_kernel : "none"; }
 
 int mb_buf_alloc(mb_ctx *h, size_t bytes, void **p) {

@@ -75,6 +75,7 @@ struct Ctx {
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
+  int64_t aux_launches = 0;  // of those: conditional follow-ups of the checked kernels, post-map passes, ghost fills
   const char *last_kernel = "none";
   int num_sms = 148;
   int force_generic = 0;   // mb_ctx_set_option("force_generic")

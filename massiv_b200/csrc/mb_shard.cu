@@ -642,6 +642,7 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
           unsigned char *dst = (unsigned char *)bufs[b] + (size_t)(side == 0 ? j : g.lo + g.local + j) * g.plane_bytes;
           fill_plane_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(dst, plane_elems, dp->p.esize, fill_bits);
           c->launches++;
+          c->aux_launches++;
         }
     }
   MB_CUDA(c, cudaGetLastError());

@@ -398,6 +398,11 @@ class Device:
         return self._L.mb_launch_count(self._h)
 
     @property
+    def aux_launch_count(self) -> int:
+        """of launch_count: conditional follow-ups of the checked kernels, post-map passes, ghost fills"""
+        return self._L.mb_aux_launch_count(self._h)
+
+    @property
     def last_kernel(self) -> str:
         return self._L.mb_last_kernel(self._h).decode()
 
