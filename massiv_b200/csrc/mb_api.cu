@@ -96,6 +96,52 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
   return st;
 }
 
+// Arrays of rank 3-5 whose stencil has extent 1 in the leading dimensions (a 2-D stencil applied to every
+// slice of a stack, a 3-D one to every volume of a batch): the tiled rank-2 / rank-3 kernels run once per
+// slice on a reduced plan.  -1 (and nothing launched) when the shape is not of that kind or the tiled
+// kernels would not take the slices.
+static int launch_batched(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  const Plan &p = dp.p;
+  if (p.rank < 3 || p.kind == MB_TAPS || p.kind == MB_LIFE) return -1;
+  int lead = 0;
+  while (lead < p.rank && p.size[lead] == 1 && p.geom[lead] == 1 && p.stride[lead] == 1 && p.shift[lead] == 0 &&
+         p.out_dims[lead] == p.in_dims[lead] && p.pad_lo[lead] == 0 && p.pad_hi[lead] == 0) ++lead;
+  if (lead > p.rank - 2) lead = p.rank - 2;
+  const int inner = p.rank - lead;
+  if (lead < 1 || inner > 3) return -1;
+  mb_stencil_desc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.kind = p.kind; rd.elem = p.elem; rd.rank = inner; rd.border = p.border; rd.flags = p.flags;
+  int64_t in_slice = 1, out_slice = 1, batch = 1, per_outer = 1;
+  for (int i = 0; i < lead; ++i) { batch *= p.in_dims[i]; if (i > 0) per_outer *= p.in_dims[i]; }
+  for (int i = 0; i < inner; ++i) {
+    const int j = lead + i;
+    rd.size[i] = p.size[j]; rd.center[i] = p.center[j]; rd.pad_lo[i] = p.pad_lo[j]; rd.pad_hi[i] = p.pad_hi[j];
+    rd.stride[i] = p.stride[j];
+    in_slice *= p.in_dims[j]; out_slice *= p.out_dims[j];
+  }
+  std::memcpy(rd.fill, p.fill, 8);
+  rd.coeffs = p.c1.empty() ? nullptr : p.c1.data();
+  rd.coeffs2 = p.c2.empty() ? nullptr : p.c2.data();
+  if (out_slice < c->tile_min_elems || batch > 65536 || batch < 1) return -1;
+  std::shared_ptr<DevPlan> sub;
+  if (get_dev_plan(c, &rd, &p.in_dims[lead], &sub) != MB_OK) return -1;
+  int64_t b0 = 0, b1 = batch;
+  if (range) { b0 = range->o0 * per_outer; b1 = range->o1 * per_outer; }
+  const size_t ib = (size_t)in_slice * p.esize, ob = (size_t)out_slice * p.esize;
+  for (int64_t b = b0; b < b1; ++b) {
+    const char *in = (const char *)d_in + (size_t)b * ib;
+    char *out = (char *)d_out + (size_t)b * ob;
+    int st = inner == 2 ? launch_tile2d(c, *sub, in, out, nullptr) : launch_vol3d(c, *sub, in, out, nullptr);
+    if (st == -1) {
+      if (b == b0) return -1;  // not a shape the tiled kernels cover: nothing has been launched
+      st = launch_generic(c, *sub, in, out, nullptr);
+    }
+    if (st) return st;
+  }
+  return MB_OK;
+}
+
 static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   if (!c->force_generic) {
     int st = range ? -1 : launch_life(c, dp, d_in, d_out);  // the Life kernels produce whole arrays
@@ -107,6 +153,8 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
     st = launch_linescan(c, dp, d_in, d_out, range);
     if (st != -1) return st;
     st = launch_direct2d(c, dp, d_in, d_out, range);
+    if (st != -1) return st;
+    st = launch_batched(c, dp, d_in, d_out, range);
     if (st != -1) return st;
   }
   return launch_generic(c, dp, d_in, d_out, range);
