@@ -33,11 +33,11 @@ def main(rep):
         tot = sum(s for s, _ in stalls) or 1.0
         print("  warp stall samples:", ", ".join(f"{n} {100 * s / tot:.1f}%" for s, n in sorted(stalls, reverse=True)[:8]))
         try:
-            rd, wr = float(d["dram__bytes_read.sum"][0]), float(d["dram__bytes_write.sum"][0])
-            t = float(d["gpu__time_duration.sum"][0])
-            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_read.sum"][1]]
-            tu = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[d["gpu__time_duration.sum"][1]]
-            print(f"  dram traffic {(rd + wr) * unit / 1e9:.3f} GB in {t * tu * 1e3:.3f} ms = {(rd + wr) * unit / (t * tu) / 1e9:.0f} GB/s (under ncu, cold, serialised)")
+            units = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+            rd = float(d["dram__bytes_read.sum"][0]) * units[d["dram__bytes_read.sum"][1]]
+            wr = float(d["dram__bytes_write.sum"][0]) * units[d["dram__bytes_write.sum"][1]]
+            t = float(d["gpu__time_duration.sum"][0]) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[d["gpu__time_duration.sum"][1]]
+            print(f"  dram traffic {(rd + wr) / 1e9:.3f} GB in {t * 1e3:.3f} ms = {(rd + wr) / t / 1e9:.0f} GB/s (under ncu, cold, serialised)")
         except Exception:
             pass
 
