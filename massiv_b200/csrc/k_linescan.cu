@@ -15,6 +15,7 @@
 // bit-identical.  The border rule applies along D only (the window has no extent elsewhere).
 #include "mb_arith.cuh"
 #include "mb_internal.h"
+#include "mb_tma.cuh"
 
 namespace mb {
 
@@ -93,14 +94,6 @@ template <typename T, int OP> struct Fold {
     return A::store(r);
   }
 };
-
-// asynchronous global -> shared copy of one element (4 or 8 bytes): no register staging, so a lane can
-// have its whole share of a span in flight at once
-template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <typename T> __device__ __forceinline__ T ls_fill(const LSParams &P) {
   T v;

@@ -134,9 +134,32 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
     mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
     tma_load_2d(smem + s * C::STAGE, &tmap, &full[s], ox0 + P.shift_x - XOFF, oy0 + P.shift_y);
   };
-  if (tid == 0) {
-    for (int i = 0; i < C::S - 1 && i < my_tiles; ++i) issue(i);
-  }
+  // Arrays TMA cannot describe (row pitch not a multiple of 16 bytes): boxes that lie inside the array are
+  // staged with cp.async by all threads, one commit group per tile, S - 1 tiles ahead like the TMA ring.
+  auto box_inside = [&](int oy0, int ox0) -> bool {
+    const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - XOFF;
+    return by0 >= 0 && bx0 >= 0 && by0 + C::BH <= P.in_h && bx0 + C::BW <= P.in_w;
+  };
+  auto prefetch = [&](int i) {  // every thread
+    if (P.use_tma) {
+      if (tid == 0 && i < my_tiles) issue(i);
+      return;
+    }
+    if (sizeof(T) >= 4 && i < my_tiles) {
+      int oy0, ox0;
+      tile_origin(i, oy0, ox0);
+      if (box_inside(oy0, ox0)) {
+        T *dst = reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE);
+        const T *src = in + (size_t)(oy0 + P.shift_y) * P.in_w + (ox0 + P.shift_x - XOFF);
+        for (int r = tid / 32; r < C::BH; r += 8)
+          for (int c = tid % 32; c < C::BW; c += 32)
+            cp_async_elem<(sizeof(T) >= 4 ? (int)sizeof(T) : 4)>(dst + r * C::BW + c, src + (size_t)r * P.in_w + c);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int i = 0; i < C::S - 1; ++i) prefetch(i);
   T fillv;
   {
     unsigned long long b = P.fill_bits;
@@ -149,16 +172,18 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
     const int s = i % C::S;
     int oy0, ox0;
     tile_origin(i, oy0, ox0);
-    if (tid == 0 && i + C::S - 1 < my_tiles) {
-      fence_proxy_async();
-      issue(i + C::S - 1);
-    }
+    if (P.use_tma && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
+    prefetch(i + C::S - 1);
     T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
     const bool by_tma = tma_ok(oy0, ox0);
     if (by_tma) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
+    } else if (!P.use_tma && sizeof(T) >= 4 && box_inside(oy0, ox0)) {
+      cp_async_wait_group<C::S - 1>();  // this tile's group has landed (S - 1 younger ones may be in flight)
+      __syncthreads();
     } else {
+      if (!P.use_tma) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
       // peeled edge path: every box cell through the border rule (Core/Index.hs:236-253)
       const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - XOFF;
       for (int e = tid; e < C::BW * C::BH; e += 256) {

@@ -126,6 +126,16 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
+// ---- cp.async (LDGSTS): the staging path for arrays TMA cannot describe (row pitch not a multiple of
+// 16 bytes, e.g. an odd number of Floats per row) ----
+// one element (4 or 8 bytes) global -> shared, no register staging; src_bytes = 0 writes zeros instead
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src, int src_bytes = BYTES) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -1,0 +1,79 @@
+"""Arrays TMA cannot describe (row pitch not a multiple of 16 bytes: odd row lengths) and the `no_tma` switch:
+the tiled kernels stage their boxes with cp.async instead.  Results against the oracle, bit-exact."""
+import zlib
+
+import numpy as np
+import pytest
+
+import massiv_b200 as M
+from helpers import bits_equal, border_obj
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+BORDERS = ["fill", "wrap", "edge", "reflect", "continue"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = M.Device.default()
+    d.set_option("tile_min_elems", 0)
+    d.set_option("force_generic", 0)
+    yield d
+    d.set_option("tile_min_elems", 16384)
+    d.set_option("no_tma", 0)
+
+
+CASES2D = [("avg", (3, 3), "f64"), ("avg", (3, 3), "f32"), ("conv", (5, 5), "f32"), ("corr", (3, 3), "f64"), ("sum", (7, 7), "f64"),
+           ("max", (3, 3), "i32"), ("mag2", (3, 3), "f32"), ("conv", (1, 5), "f64"), ("product", (2, 2), "f32")]
+
+
+@pytest.mark.parametrize("kind,size,elem", CASES2D)
+@pytest.mark.parametrize("no_tma", [0, 1])
+def test_2d_odd_pitches(dev, kind, size, elem, no_tma):
+    dev.set_option("no_tma", no_tma)
+    dt = np.dtype(O.ELEM2NP[elem])
+    rng = np.random.default_rng(zlib.crc32(repr((kind, size, elem)).encode()))
+    n = int(np.prod(size))
+    co = rng.standard_normal(n).astype(dt).tolist() if kind in ("conv", "corr", "mag2") else None
+    co2 = rng.standard_normal(n).astype(dt).tolist() if kind == "mag2" else None
+    for shape in ((131, 203), (200, 517), (97, 130), (260, 1001)):
+        arr = (rng.standard_normal(shape) * (0.2 if kind == "product" else 1) + (1 if kind == "product" else 0)).astype(dt) \
+            if dt.kind == "f" else rng.integers(-999, 999, size=shape).astype(dt)
+        for border in BORDERS:
+            want = O.apply(kind, arr, size=size, border=border, fill=2, coeffs=co, coeffs2=co2)
+            st = M.Stencil(kind, size, None, None if co is None else np.asarray(co, dt).reshape(size),
+                           None if co2 is None else np.asarray(co2, dt).reshape(size))
+            got = M.compute(M.mapStencil(border_obj(border, 2), st, dev.fromHost(arr))).toHost()
+            assert dev.last_kernel.startswith("tile2d"), dev.last_kernel
+            assert bits_equal(got, want), (shape, border)
+    dev.set_option("no_tma", 0)
+
+
+@pytest.mark.parametrize("no_tma", [0, 1])
+@pytest.mark.parametrize("elem", ["f64", "f32"])
+def test_3d_odd_pitches(dev, elem, no_tma):
+    dev.set_option("no_tma", no_tma)
+    dt = np.dtype(O.ELEM2NP[elem])
+    rng = np.random.default_rng(5 + no_tma)
+    k = np.zeros((3, 3, 3), dt)
+    k[1, 1, 1], k[0, 1, 1], k[2, 1, 1], k[1, 0, 1], k[1, 2, 1], k[1, 1, 0], k[1, 1, 2] = 0.4, .1, .1, .1, .1, .1, .1
+    kr = rng.standard_normal((3, 3, 3)).astype(dt)
+    for shape in ((20, 37, 71), (13, 66, 133), (40, 33, 65)):
+        arr = rng.random(shape).astype(dt)
+        for kk in (k, kr):
+            co = kk.reshape(-1).tolist()
+            for border in BORDERS:
+                want = O.apply("conv", arr, size=(3, 3, 3), coeffs=co, border=border, fill=0.0)
+                got = M.compute(M.mapStencil(border_obj(border, 0.0), M.makeConvolutionStencilFromKernel(kk), dev.fromHost(arr))).toHost()
+                assert dev.last_kernel.startswith("vol3d"), dev.last_kernel
+                assert bits_equal(got, want), (shape, border)
+        for n in (2, 3, 5):
+            want = O.iterate("conv", arr, n, size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border="fill", fill=0.0)
+            got = M.iterateStencil(n, M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), dev.fromHost(arr)).toHost()
+            assert bits_equal(got, want), (shape, n)
+            a2 = arr.copy()
+            a2[shape[0] // 2, 5, shape[2] - 1] = np.inf
+            want = O.iterate("conv", a2, n, size=(3, 3, 3), coeffs=k.reshape(-1).tolist(), border="fill", fill=0.0)
+            got = M.iterateStencil(n, M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), dev.fromHost(a2)).toHost()
+            assert bits_equal(got, want), (shape, n, "inf")
+    dev.set_option("no_tma", 0)
