@@ -38,6 +38,7 @@ struct TB2Params {
   int z0, z1;            // result planes produced
   int tiles_x, tiles_y, zc, nitems;
   int vec_store;
+  int use_tma;           // 0: the array cannot be described to TMA; boxes are staged with cp.async (zero fill by hand)
 };
 
 template <typename T> struct Coef27b {
@@ -109,10 +110,10 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
 // clear).  DETECT 2 inspects every source and intermediate value.  DETECT 1 (centre coefficient non-zero)
 // inspects the RESULTS only: a non-finite value at a cell makes the next application's value at the same
 // cell non-finite through the centre tap, so it always surfaces in the result tile that owns the cell.
-template <typename T, bool REV, int R_, int DETECT>
+template <typename T, bool REV, int R_, int DETECT, bool TMA>
 __global__ void __launch_bounds__(256, MB_TB2_MINB)
-vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, T *__restrict__ out,
-                 unsigned *flag) {
+vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, const T *__restrict__ in,
+                 T *__restrict__ out, unsigned *flag) {
   unsigned bad = 0;
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
@@ -122,7 +123,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   uint64_t *ufree = full + S;  // "every warp has read intermediate buffer b": it may be overwritten
   const int tid = threadIdx.x;
   if (tid == 0) {
-    tma_prefetch_desc(&tmap);
+    if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_init(&ufree[0], 8);
@@ -145,7 +146,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   // consumes nz + 4 source planes (two above, two below).  The next load's coordinates are kept
   // incrementally so that the steady state costs a handful of instructions.
   int p_it = 0, p_left = 0, p_x = 0, p_y = 0, p_z = 0, issued = 0, total_loads = 0;
-  if (tid == 0) {
+  if (tid == 0 || !TMA) {  // (without TMA every thread keeps the producer's books: all of them copy)
     for (int it = 0; it < my_items; ++it) {
       int a, nz, b, c;
       item_geom(it, a, nz, b, c);
@@ -161,18 +162,44 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
         p_x = ox0 - 2 * V; p_y = oy0 - 2; p_z = oz0 + P.sz2 - 2;
       }
       const int s = issued % S;
-      mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
-      tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], p_x, p_y, p_z);
+      if (TMA) {
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
+        tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], p_x, p_y, p_z);
+      } else {
+        // the whole CTA copies the box; cells outside the array are written as zeros (src-size 0), which
+        // is what TMA's out-of-range fill does.  One commit group per plane.
+        T *dst = reinterpret_cast<T *>(smem + s * C::STAGE);
+        const bool z_ok = p_z >= 0 && p_z < P.in_d;
+        for (int e = tid; e < C::BW * C::BH; e += 256) {
+          const int r = e / C::BW, cc = e - r * C::BW;
+          const int gy = p_y + r, gx = p_x + cc;
+          const bool ok = z_ok && gy >= 0 && gy < P.in_h && gx >= 0 && gx < P.in_w;
+          const T *src = ok ? in + ((size_t)p_z * P.in_h + gy) * P.in_w + gx : in;
+          cp_async_elem<(int)sizeof(T)>(dst + e, src, ok ? (int)sizeof(T) : 0);
+        }
+        cp_async_commit();
+      }
       ++issued; ++p_z; --p_left;
     }
   };
-  if (tid == 0) issue_upto(S);
+  if (tid == 0 || !TMA) issue_upto(S);
 
   uint32_t phase = 0;
   auto acquire = [&](int L) {
     const int s = L % S;
-    mbar_wait(&full[s], (phase >> s) & 1u);
-    phase ^= 1u << s;
+    if (TMA) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      // plane L's group must have landed; issued - 1 - L younger groups may still be in flight
+      switch (issued - 1 - L) {
+        case 0: cp_async_wait_group<0>(); break;
+        case 1: cp_async_wait_group<1>(); break;
+        case 2: cp_async_wait_group<2>(); break;
+        default: cp_async_wait_group<3>(); break;
+      }
+      __syncthreads();  // everybody's share of the plane is visible
+    }
   };
   const int lx = (tid % 32) * V, ly = (tid / 32) * R;
   const int coff = (ly + 1) * BW + V + lx;  // the thread's first cell inside a staged box
@@ -255,7 +282,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
         *reinterpret_cast<uint4 *>(ub + r * BW) = q;
       }
       __syncthreads();  // intermediate plane ip is complete; source plane ip (the middle one) is no longer read
-      if (tid == 0) issue_upto(((k == nz + 1) ? Lc + nz + 4 : Lc + k + 2) + S);
+      if (tid == 0 || !TMA) issue_upto(((k == nz + 1) ? Lc + nz + 4 : Lc + k + 2) + S);
       // ---- stage 2: second application one plane behind, intermediate planes ip-2, ip-1, ip ----
       const T *umid = reinterpret_cast<const T *>(ubase + ((g + 1u) & 1u) * C::STAGE) + coff;
       if (k >= 2) {
@@ -322,10 +349,12 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
-  if (c->no_tma || !make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) return -1;
-  auto kern = vol3d_tb2_kernel<T, REV, R_, DETECT>;
-  static int occ_dev[64] = {0};
-  int &occ = occ_dev[c->device & 63];
+  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
+  auto kern_tma = vol3d_tb2_kernel<T, REV, R_, DETECT, true>;
+  auto kern_cp = vol3d_tb2_kernel<T, REV, R_, DETECT, false>;
+  auto kern = P.use_tma ? kern_tma : kern_cp;
+  static int occ_dev[64][2] = {{0}};
+  int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
@@ -351,7 +380,7 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   }
   P.nitems = tiles * chunks;
   const int grid = resident < P.nitems ? resident : P.nitems;
-  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (T *)d_out, flag);
+  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out, flag);
   c->launches++;
   c->last_kernel = "vol3d_tb2";
   return check_cuda(c, cudaGetLastError(), "vol3d_tb2_kernel launch");
@@ -388,7 +417,7 @@ bool tb2_desc_eligible(const mb_stencil_desc *d) {
 // 1: yes, under the caller's finite promise; 2: yes, optimistically — the kernel checks what the promise
 // would have covered and the caller redoes the pair strictly when the check fails; 0: no.
 int vol3d_tb2_mode(Ctx *c, const Plan &p) {
-  if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return 0;
+  if (!c->tb2 || c->force_generic || !p.post.empty()) return 0;
   if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return 0;
   if (p.border != MB_FILL) return 0;
   for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) return 0;
@@ -414,8 +443,7 @@ int vol3d_tb2_slab_mode(Ctx *c, const Plan &p) {
 
 bool vol3d_tb2_applicable(Ctx *c, const Plan &p) {
   if (!(p.flags & MB_FLAG_ASSUME_FINITE)) return false;
-  if ((p.in_dims[2] * p.esize) % 16 != 0) return false;  // TMA: row pitch in whole 16-byte units
-  if (!c->tb2 || c->force_generic || c->no_tma || !p.post.empty()) return false;
+  if (!c->tb2 || c->force_generic || !p.post.empty()) return false;
   if (p.rank != 3 || !p.unit_stride() || (p.kind != MB_CONV && p.kind != MB_CORR)) return false;
   if (p.border != MB_FILL) return false;
   for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) return false;
