@@ -68,7 +68,7 @@ template <typename T> __device__ __forceinline__ void lds_vec(T *dst, const T *s
 // makes the result at its own position non-finite through the centre tap (Inf * k, NaN * k; nothing
 // added to it brings it back).  The dense kernel that follows on the stream takes `flag` as its condition
 // and returns at once when it is clear, so the strict result costs a star pass for finite data.
-template <typename T, int MODE, bool REV, int DETECT>
+template <typename T, int MODE, bool REV, int DETECT, bool TMA>
 __global__ void __launch_bounds__(256, MODE == V3_STAR7 ? MB_V3_MINB : 1)
 vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const Coef27<T> K,
              const T *__restrict__ in, T *__restrict__ out, unsigned *flag) {
@@ -81,7 +81,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * C::STAGE);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    if (P.use_tma) tma_prefetch_desc(&tmap);
+    if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
@@ -100,14 +100,22 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
   };
   // may the plane box be fetched by TMA (out-of-range cells unused, or zero IS the border)?
   auto tma_ok = [&](int zsrc, int oy0, int ox0) -> bool {
-    if (!P.use_tma) return false;
+    if (!TMA) return false;
     if (P.zero_fill_ok) return true;
     const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - 1;
     const int th = min(C::TY, P.out_h - oy0), tw = min(C::TX, P.out_w - ox0);
     return zsrc >= 0 && zsrc < P.in_d && y0 >= 0 && x0 >= 0 && y0 + th + 2 <= P.in_h && x0 + tw + 2 <= P.in_w;
   };
 
-  // ---- producer state (thread 0): loads are numbered globally, stage = number % S ----
+  // without TMA: may the plane box be staged with cp.async (cells outside the array written as zeros)?
+  auto cp_ok = [&](int zsrc, int oy0, int ox0) -> bool {
+    if (TMA) return false;
+    if (P.zero_fill_ok) return true;
+    const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - V;
+    return zsrc >= 0 && zsrc < P.in_d && y0 >= 0 && x0 >= 0 && y0 + C::BH <= P.in_h && x0 + C::BW <= P.in_w;
+  };
+
+  // ---- producer state (thread 0; every thread without TMA): loads are numbered globally, stage = number % S ----
   int p_it = 0, p_pl = 0, issued = 0, released = 0;
   int total_loads = 0;
   for (int it = 0; it < my_items; ++it) {
@@ -124,10 +132,25 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
       mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
       tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], ox0 + P.sx - V, oy0 + P.sy - 1, zsrc);
     }
+    if (!TMA) {  // one commit group per load, empty when the box goes through the border rule at acquire time
+      if (cp_ok(zsrc, oy0, ox0)) {
+        T *dst = reinterpret_cast<T *>(smem + s * C::STAGE);
+        const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - V;
+        const bool z_ok = zsrc >= 0 && zsrc < P.in_d;
+        for (int e = tid; e < C::BW * C::BH; e += 256) {
+          const int r = e / C::BW, cc = e - r * C::BW;
+          const int gy = y0 + r, gx = x0 + cc;
+          const bool ok = z_ok && gy >= 0 && gy < P.in_h && gx >= 0 && gx < P.in_w;
+          const T *src = ok ? in + ((size_t)zsrc * P.in_h + gy) * P.in_w + gx : in;
+          cp_async_elem<(int)sizeof(T)>(dst + e, src, ok ? (int)sizeof(T) : 0);
+        }
+      }
+      cp_async_commit();
+    }
     ++issued;
     if (++p_pl == nz + 2) { p_pl = 0; ++p_it; }
   };
-  if (tid == 0) {
+  if (tid == 0 || !TMA) {
     while (issued < total_loads && issued < released + S) issue_next();
   }
 
@@ -143,6 +166,16 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
     if (tma_ok(zsrc, oy0, ox0)) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
+    } else if (cp_ok(zsrc, oy0, ox0)) {
+      switch (issued - 1 - L) {  // younger groups that may still be in flight
+        case 0: cp_async_wait_group<0>(); break;
+        case 1: cp_async_wait_group<1>(); break;
+        case 2: cp_async_wait_group<2>(); break;
+        case 3: cp_async_wait_group<3>(); break;
+        case 4: cp_async_wait_group<4>(); break;
+        default: cp_async_wait_group<5>(); break;
+      }
+      __syncthreads();
     } else {
       T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
       const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - V;
@@ -249,7 +282,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
 #pragma unroll
           for (int v = 0; v < V; ++v) { zm[r][v] = zc[r][v]; zc[r][v] = zp[r][v]; }
         __syncthreads();  // plane Lc+j+1 (the middle one) is no longer read by anyone
-        if (tid == 0) {
+        if (tid == 0 || !TMA) {
           released = (j == nz - 1) ? Lc + nz + 2 : Lc + j + 2;
           while (issued < total_loads && issued < released + S) issue_next();
         }
@@ -272,7 +305,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
       load_win(w[0], Lc);
       load_win(w[1], Lc + 1);
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 || !TMA) {
         released = Lc + 2;
         while (issued < total_loads && issued < released + S) issue_next();
       }
@@ -321,7 +354,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
 #pragma unroll
           for (int v = 0; v < V + 2; ++v) { w[0][r][v] = w[1][r][v]; w[1][r][v] = w[2][r][v]; }
         __syncthreads();  // the newest plane now lives in registers: its stage is free
-        if (tid == 0) {
+        if (tid == 0 || !TMA) {
           released = Lc + j + 3;
           while (issued < total_loads && issued < released + S) issue_next();
         }
@@ -358,9 +391,11 @@ static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, c
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
   P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
-  auto kern = vol3d_kernel<T, MODE, REV, DETECT>;
-  static int occ_dev[64] = {0};
-  int &occ = occ_dev[c->device & 63];
+  auto kern_tma = vol3d_kernel<T, MODE, REV, DETECT, true>;
+  auto kern_cp = vol3d_kernel<T, MODE, REV, DETECT, false>;
+  auto kern = P.use_tma ? kern_tma : kern_cp;
+  static int occ_dev[64][2] = {{0}};
+  int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
