@@ -78,8 +78,32 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
     tma_load_2d(smem + s * C::STAGE, &tmap, &full[s], ox0 + P.shift_x - XOFF, oy0 + P.shift_y);
   };
-  if (tid == 0)
-    for (int i = 0; i < C::S - 1 && i < my_tiles; ++i) issue(i);
+  // arrays TMA cannot describe: boxes inside the array are staged with cp.async by all threads, one commit
+  // group per tile, S - 1 tiles ahead like the TMA ring (see k_tile2d.cuh)
+  auto box_inside = [&](int oy0, int ox0) -> bool {
+    const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - XOFF;
+    return by0 >= 0 && bx0 >= 0 && by0 + C::BH <= P.h && bx0 + C::BW <= P.w;
+  };
+  auto prefetch = [&](int i) {
+    if (P.use_tma) {
+      if (tid == 0 && i < my_tiles) issue(i);
+      return;
+    }
+    if (i < my_tiles) {
+      int oy0, ox0;
+      tile_origin(i, oy0, ox0);
+      if (box_inside(oy0, ox0)) {
+        T *dst = reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE);
+        const T *src = in + (size_t)(oy0 + P.shift_y) * P.w + (ox0 + P.shift_x - XOFF);
+        for (int r = tid / 32; r < C::BH; r += 8)
+          for (int c = tid % 32; c < C::BW; c += 32)
+            cp_async_elem<(int)sizeof(T)>(dst + r * C::BW + c, src + (size_t)r * P.w + c);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int i = 0; i < C::S - 1; ++i) prefetch(i);
   T fillv;
   {
     unsigned long long b = P.fill_bits;
@@ -93,17 +117,19 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     const int s = i % C::S;
     int oy0, ox0;
     tile_origin(i, oy0, ox0);
-    if (tid == 0 && i + C::S - 1 < my_tiles) {
-      fence_proxy_async();
-      issue(i + C::S - 1);
-    }
+    if (P.use_tma && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
+    prefetch(i + C::S - 1);
     T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
     const bool by_tma = tma_ok(oy0, ox0);
     const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - XOFF;
     if (by_tma) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
+    } else if (!P.use_tma && box_inside(oy0, ox0)) {
+      cp_async_wait_group<C::S - 1>();
+      __syncthreads();
     } else {
+      if (!P.use_tma) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
       for (int e = tid; e < C::BW * C::BH; e += 256) {
         const int r = e / C::BW, c = e - r * C::BW;
         int gy = by0 + r, gx = bx0 + c;

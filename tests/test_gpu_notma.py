@@ -77,3 +77,21 @@ def test_3d_odd_pitches(dev, elem, no_tma):
             got = M.iterateStencil(n, M.Fill(0.0), M.makeConvolutionStencilFromKernel(k), dev.fromHost(a2)).toHost()
             assert bits_equal(got, want), (shape, n, "inf")
     dev.set_option("no_tma", 0)
+
+
+@pytest.mark.parametrize("no_tma", [0, 1])
+def test_separable_odd_pitches(dev, no_tma):
+    dev.set_option("no_tma", no_tma)
+    rng = np.random.default_rng(31)
+    for dt, K in ((np.float32, 7), (np.float64, 5), (np.float32, 3)):
+        g = rng.standard_normal(K).astype(dt)
+        for shape in ((130, 203), (97, 517)):
+            img = rng.random(shape).astype(dt)
+            for border in BORDERS:
+                t = O.apply("conv", img, size=(1, K), coeffs=g.tolist(), border=border, fill=0.5)
+                want = O.apply("conv", t, size=(K, 1), coeffs=g.tolist(), border=border, fill=0.5)
+                row, col = M.makeConvolutionStencilFromKernel(g.reshape(1, K)), M.makeConvolutionStencilFromKernel(g.reshape(K, 1))
+                got = M.computeSeparable(border_obj(border, 0.5), row, col, dev.fromHost(img)).toHost()
+                assert dev.last_kernel == "sep2d", dev.last_kernel
+                assert bits_equal(got, want), (shape, border)
+    dev.set_option("no_tma", 0)
