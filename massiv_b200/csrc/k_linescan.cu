@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) linescan_cols_kernel(const LSParams P, co
 template <typename T, int OP, bool SPAN>
 __global__ void __launch_bounds__(256) linescan_rows_kernel(const LSParams P, const T *__restrict__ in, T *__restrict__ out,
                                                               int CH, int PITCH, int64_t nseg, int64_t nitems, int PAD,
-                                                              int sshift, int buf_elems) {
+                                                              int sshift, int buf_elems, int OPL) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *buf = reinterpret_cast<T *>(smem_raw) + (size_t)warp * buf_elems;
@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(256) linescan_rows_kernel(const LSParams P, co
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t item = blockIdx.x * (int64_t)(blockDim.x >> 5) + warp; item < nitems; item += wstride) {
     const int64_t row = item / nseg, seg = item - row * nseg;
-    const int64_t o0 = seg * 32;
-    const int nout = (int)min((int64_t)32, (int64_t)(P.OD - o0));
+    const int per_item = 32 * OPL;  // outputs per item: OPL per lane (short windows need more than 32 to amortise an item)
+    const int64_t o0 = seg * per_item;
+    const int nout = (int)min((int64_t)per_item, (int64_t)(P.OD - o0));
     const T *src = in + row * P.D;
     const int64_t x0 = o0 * P.s + P.shift;  // window element 0 of the segment's first output
     const bool inside = x0 >= 0 && x0 + (int64_t)(nout - 1) * P.s + P.K <= P.D;
@@ -185,11 +186,15 @@ __global__ void __launch_bounds__(256) linescan_rows_kernel(const LSParams P, co
         }
       }
       __syncwarp();
-      if (lane < nout) {
-        const T *w = buf + lane * (si + PAD);
-        f.run([&](int i) { return w[i + (i >= si ? PAD : 0)]; }, P.K);
+      for (int oj = lane; oj < nout; oj += 32) {
+        const T *w = buf + oj * (si + PAD);
+        Fold<T, OP> g;
+        g.init();
+        g.run([&](int i) { return w[i + (i >= si ? PAD : 0)]; }, P.K);
+        out[row * P.OD + o0 + oj] = g.finish(P);
       }
       __syncwarp();
+      continue;
     } else {
       for (int c0 = 0; c0 < P.K; c0 += CH) {
         const int L = min(CH, P.K - c0);
@@ -197,6 +202,14 @@ __global__ void __launch_bounds__(256) linescan_rows_kernel(const LSParams P, co
         // elements of a piece; several loads are issued before the first store (requests in flight)
         constexpr int U = 8;
         int j = lane / L, i = lane - j * L;
+        if (sizeof(T) >= 4 && inside) {
+          while (j < nout) {  // no register staging: every copy of the lane's share is in flight at once
+            cp_async_elem<(sizeof(T) >= 4 ? (int)sizeof(T) : 4)>(&buf[j * PITCH + i], &src[x0 + (int64_t)j * P.s + c0 + i]);
+            i += 32;
+            while (i >= L) { i -= L; ++j; }
+          }
+          cp_async_wait_all();
+        }
         while (j < nout) {
           int pos[U];
           T v[U];
@@ -239,14 +252,15 @@ static int launch_ls(Ctx *c, const LSParams &P, const void *d_in, void *d_out) {
   } else {
     const int CH = P.K < 32 ? P.K : 32;
     const int PITCH = CH | 1;
-    const int64_t nseg = (P.OD + 31) / 32, nitems = P.A * nseg;
     const bool span = P.K <= P.s + 1 && P.s <= 64;
-    int PAD = 0, sshift = -1, buf_elems = 32 * PITCH;
+    int PAD = 0, sshift = -1, buf_elems = 32 * PITCH, OPL = 1;
     if (span) {
       PAD = (P.s % 2 == 0) ? 1 : 0;
       for (int b = 0; b < 7; ++b) if (((int64_t)1 << b) == P.s) sshift = b;
-      buf_elems = 31 * (int)P.s + P.K + 32 * PAD + 1;
+      OPL = (int)std::max<int64_t>(1, std::min<int64_t>(8, 512 / (32 * P.s)));  // ~512 elements per item and warp
+      buf_elems = (32 * OPL - 1) * (int)P.s + P.K + 32 * OPL * PAD + 1;
     }
+    const int64_t nseg = (P.OD + 32 * OPL - 1) / (32 * OPL), nitems = P.A * nseg;
     const size_t smem = (size_t)8 * buf_elems * sizeof(T);
     int64_t blocks = (nitems + 7) / 8;
     const int64_t cap = (int64_t)c->num_sms * 8;
@@ -257,7 +271,7 @@ static int launch_ls(Ctx *c, const LSParams &P, const void *d_in, void *d_out) {
       MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (31 * 64 + 65 + 33) * (int)sizeof(T)));
       attr_set[c->device & 63][span] = true;
     }
-    kern<<<(unsigned)blocks, 256, smem, c->stream>>>(P, (const T *)d_in, (T *)d_out, CH, PITCH, nseg, nitems, PAD, sshift, buf_elems);
+    kern<<<(unsigned)blocks, 256, smem, c->stream>>>(P, (const T *)d_in, (T *)d_out, CH, PITCH, nseg, nitems, PAD, sshift, buf_elems, OPL);
     c->last_kernel = "linescan_rows";
   }
   c->launches++;
