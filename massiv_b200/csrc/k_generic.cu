@@ -9,17 +9,30 @@
 namespace mb {
 
 struct GParams {
-  int rank, border, kind, bool_canon, skip_zero;
+  int rank, border, kind, bool_canon, skip_zero, small;
   int64_t in_dims[MB_MAX_RANK], out_dims[MB_MAX_RANK], stride[MB_MAX_RANK], shift[MB_MAX_RANK];
   int64_t ntaps, cell0, ncells, avg_n;
+  int64_t min_off[MB_MAX_RANK], max_off[MB_MAX_RANK];
   const int32_t *taps;
+  const int64_t *tap_lin;
   const void *c1, *c2;
   unsigned long long fill_bits;
 };
 
+// a cell whose whole window lies inside the array reads its taps at precomputed linear offsets
+struct Cell {
+  bool interior;
+  int64_t lin;
+};
+
 template <typename T>
 __device__ __forceinline__ T fetch(const GParams &P, const T *__restrict__ in, const int64_t *ix,
-                                   const int32_t *__restrict__ off, T fillv) {
+                                   const int32_t *__restrict__ off, T fillv, const Cell &cell, int64_t t) {
+  if (cell.interior) {
+    T v = in[cell.lin + P.tap_lin[t]];
+    if (P.bool_canon) v = (T)(v != T(0));
+    return v;
+  }
   int64_t lin = 0;
 #pragma unroll 1
   for (int d = 0; d < P.rank; ++d) {
@@ -46,41 +59,58 @@ __global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *
        cell += (int64_t)gridDim.x * blockDim.x) {
     const int64_t lin_out = P.cell0 + cell;
     int64_t ix[MB_MAX_RANK];
-    {
+    if (P.small) {  // everything fits 32 bits: the 64-bit divisions are most of a cell's cost otherwise
+      unsigned rem = (unsigned)lin_out;
+#pragma unroll 1
+      for (int d = r - 1; d >= 0; --d) {
+        const unsigned od = (unsigned)P.out_dims[d];
+        const unsigned q = rem / od, j = rem - q * od;
+        rem = q;
+        ix[d] = (int64_t)j * P.stride[d] + P.shift[d];  // Stencil.hs:200 + Stride.hs:110-120
+      }
+    } else {
       int64_t rem = lin_out;
 #pragma unroll 1
       for (int d = r - 1; d >= 0; --d) {
         const int64_t j = rem % P.out_dims[d];
         rem /= P.out_dims[d];
-        ix[d] = j * P.stride[d] + P.shift[d];  // Stencil.hs:200 + Stride.hs:110-120
+        ix[d] = j * P.stride[d] + P.shift[d];
       }
     }
     const int32_t *taps = P.taps;
+    Cell win;
+    win.interior = P.tap_lin != nullptr;
+    win.lin = 0;
+#pragma unroll 1
+    for (int d = 0; d < r; ++d) {
+      win.interior = win.interior && ix[d] + P.min_off[d] >= 0 && ix[d] + P.max_off[d] < P.in_dims[d];
+      win.lin = win.lin * P.in_dims[d] + ix[d];
+    }
     T res;
     switch (P.kind) {
-      case MB_ID: res = fetch<T>(P, in, ix, taps, fillv); break;
+      case MB_ID: res = fetch<T>(P, in, ix, taps, fillv, win, 0); break;
       case MB_SUM: case MB_AVG: {
         Acc acc = A::from_count(0);
-        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)));
         if (P.kind == MB_AVG) acc = A::div(acc, A::from_count(P.avg_n));
         res = A::store(acc);
         break;
       }
       case MB_PRODUCT: {
         Acc acc = A::from_count(1);
-        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::mul(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::mul(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)));
         res = A::store(acc);
         break;
       }
       case MB_MAX: {
         T acc = P.bool_canon ? T(0) : Bounds<T>::lo();  // Bounded Bool: False..True
-        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv); acc = x > acc ? x : acc; }
+        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv, win, t); acc = x > acc ? x : acc; }
         res = acc;
         break;
       }
       case MB_MIN: {
         T acc = P.bool_canon ? T(1) : Bounds<T>::hi();
-        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv); acc = x < acc ? x : acc; }
+        for (int64_t t = 0; t < P.ntaps; ++t) { T x = fetch<T>(P, in, ix, taps + t * r, fillv, win, t); acc = x < acc ? x : acc; }
         res = acc;
         break;
       }
@@ -90,7 +120,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *
         for (int64_t t = 0; t < P.ntaps; ++t) {
           const Acc kv = A::load(k[t]);
           if (P.skip_zero && A::is_zero(kv)) continue;
-          acc = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), acc);
+          acc = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)), kv), acc);
         }
         res = A::store(acc);
         break;
@@ -101,38 +131,38 @@ __global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *
         for (int64_t t = 0; t < P.ntaps; ++t) {
           const Acc kv = A::load(k1[t]);
           if (P.skip_zero && A::is_zero(kv)) continue;
-          a = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), a);
+          a = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)), kv), a);
         }
         for (int64_t t = 0; t < P.ntaps; ++t) {
           const Acc kv = A::load(k2[t]);
           if (P.skip_zero && A::is_zero(kv)) continue;
-          b = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv)), kv), b);
+          b = A::add(A::mul(A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)), kv), b);
         }
         res = A::store(A::sqrt(A::add(A::mul(a, a), A::mul(b, b))));
         break;
       }
       case MB_INT_MIDPOINT: {  // Integral.hs:64-66: dx * loop 0 (< k) (+ 1) 0 (\i -> (+ g i))
         Acc acc = A::from_count(0);
-        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv)));
+        for (int64_t t = 0; t < P.ntaps; ++t) acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t)));
         res = A::store(A::mul(A::load(*(const T *)P.c1), acc));
         break;
       }
       case MB_INT_TRAPEZOID: {  // Integral.hs:85-89: (dx / 2) * (loop 1 (< n) .. (g 0) (+ 2 * g i) + g n)
         const int64_t n = P.ntaps - 1;
-        Acc acc = A::load(fetch<T>(P, in, ix, taps, fillv));
+        Acc acc = A::load(fetch<T>(P, in, ix, taps, fillv, win, 0));
         for (int64_t t = 1; t < n; ++t)
-          acc = A::add(acc, A::mul(A::from_count(2), A::load(fetch<T>(P, in, ix, taps + t * r, fillv))));
-        acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + n * r, fillv)));
+          acc = A::add(acc, A::mul(A::from_count(2), A::load(fetch<T>(P, in, ix, taps + t * r, fillv, win, t))));
+        acc = A::add(acc, A::load(fetch<T>(P, in, ix, taps + n * r, fillv, win, n)));
         res = A::store(A::mul(A::div(A::load(*(const T *)P.c1), A::from_count(2)), acc));
         break;
       }
       case MB_INT_SIMPSON: {  // Integral.hs:112-117: acc + prev + 4 * g (i + 1) + fx3, then dx / 3 * acc
         const int64_t n = P.ntaps - 1;
         Acc acc = A::from_count(0);
-        Acc prev = A::load(fetch<T>(P, in, ix, taps, fillv));
+        Acc prev = A::load(fetch<T>(P, in, ix, taps, fillv, win, 0));
         for (int64_t i = 0; i < n - 1; i += 2) {
-          const Acc fx3 = A::load(fetch<T>(P, in, ix, taps + (i + 2) * r, fillv));
-          const Acc mid = A::mul(A::from_count(4), A::load(fetch<T>(P, in, ix, taps + (i + 1) * r, fillv)));
+          const Acc fx3 = A::load(fetch<T>(P, in, ix, taps + (i + 2) * r, fillv, win, i + 2));
+          const Acc mid = A::mul(A::from_count(4), A::load(fetch<T>(P, in, ix, taps + (i + 1) * r, fillv, win, i + 1)));
           acc = A::add(A::add(A::add(acc, prev), mid), fx3);
           prev = fx3;
         }
@@ -141,9 +171,9 @@ __global__ void __launch_bounds__(256) generic_kernel(const GParams P, const T *
       }
       default: {  // MB_LIFE (T = uint8_t): GameOfLife.hs:15-36
         unsigned n = 0;
-        for (int t = 0; t < 8; ++t) n += (unsigned)fetch<T>(P, in, ix, taps + t * r, fillv);
+        for (int t = 0; t < 8; ++t) n += (unsigned)fetch<T>(P, in, ix, taps + t * r, fillv, win, t);
         n &= 0xFFu;
-        const unsigned c = (unsigned)fetch<T>(P, in, ix, taps + 8 * r, fillv);
+        const unsigned c = (unsigned)fetch<T>(P, in, ix, taps + 8 * r, fillv, win, 8);
         res = (T)(((c == 0 && n == 3) || (c == 1 && (n == 2 || n == 3))) ? 1 : 0);
         break;
       }
@@ -177,6 +207,9 @@ int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, con
   }
   P.ntaps = p.ntaps; P.avg_n = p.avg_n;
   P.taps = dp.d_taps; P.c1 = dp.d_c1; P.c2 = dp.d_c2;
+  P.tap_lin = dp.d_tap_lin;
+  P.small = p.out_elems < ((int64_t)1 << 31);
+  for (int i = 0; i < p.rank; ++i) { P.min_off[i] = p.min_off[i]; P.max_off[i] = p.max_off[i]; }
   std::memcpy(&P.fill_bits, p.fill, 8);
   int64_t o0 = 0, o1 = p.out_dims[0];
   if (range) { o0 = range->o0; o1 = range->o1; }

@@ -36,6 +36,7 @@ int ensure_scratch(Ctx *c, int slot, size_t bytes, void **ptr) {
 
 static void free_dev_plan(DevPlan *dp) {
   if (dp->d_taps) cudaFree(dp->d_taps);
+  if (dp->d_tap_lin) cudaFree(dp->d_tap_lin);
   if (dp->d_c1) cudaFree(dp->d_c1);
   if (dp->d_c2) cudaFree(dp->d_c2);
   delete dp;
@@ -66,6 +67,16 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
     MB_CUDA(c, cudaMalloc(&dp->d_taps, q.tap_off.size() * sizeof(int32_t)));
     MB_CUDA(c, cudaMemcpyAsync(dp->d_taps, q.tap_off.data(), q.tap_off.size() * sizeof(int32_t),
                                cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!q.tap_off.empty()) {
+    std::vector<int64_t> lin((size_t)q.ntaps);
+    for (int64_t t = 0; t < q.ntaps; ++t) {
+      int64_t l = 0;
+      for (int i = 0; i < q.rank; ++i) l = l * q.in_dims[i] + q.tap_off[(size_t)t * q.rank + i];
+      lin[(size_t)t] = l;
+    }
+    MB_CUDA(c, cudaMalloc(&dp->d_tap_lin, lin.size() * sizeof(int64_t)));
+    MB_CUDA(c, cudaMemcpy(dp->d_tap_lin, lin.data(), lin.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
   }
   if (!q.c1.empty()) {
     MB_CUDA(c, cudaMalloc(&dp->d_c1, q.c1.size()));

@@ -62,6 +62,7 @@ int border_index(int border, int64_t k, int64_t i, int64_t *out, int32_t *is_fil
 struct DevPlan {
   Plan p;
   int32_t *d_taps = nullptr;
+  int64_t *d_tap_lin = nullptr;  // the taps as linear offsets in the input (cells whose window is inside the array)
   void *d_c1 = nullptr, *d_c2 = nullptr;
 };
 
