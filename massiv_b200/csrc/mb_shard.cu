@@ -3,11 +3,14 @@
 // The reference has no distributed story (single process); this is the analogue of its
 // `iterateUntil` loop (Array/Manifest/Internal.hs:331-397) for arrays too large or too slow for one
 // GPU.  The global array is cut along the OUTERMOST dimension (contiguous in row-major, so a halo
-// plane is one contiguous block).  Per step every rank
-//   1. computes the output planes its neighbours need (the first halo_hi and last halo_lo planes),
-//   2. hands them to rank-1 / rank+1 with ncclSend/ncclRecv on a second stream,
-//   3. computes the interior planes on the main stream while the exchange is in flight,
-//   4. joins the two streams and swaps buffers.
+// plane is one contiguous block).  Per round (one step, or two fused steps for star-shaped 3-D kernels
+// under Fill 0) every rank
+//   1. takes delivery of its neighbours' planes for this round,
+//   2. computes the output planes its neighbours need (the first halo_hi and last halo_lo planes),
+//   3. ships them — peer copies over NVLink into the neighbours' staging areas with counter hand-shakes
+//      in device memory (below), or ncclSend/ncclRecv on a second stream as the fallback,
+//   4. computes the interior planes while the transfer is in flight, and swaps buffers.
+// (Promise-free fused rounds compute the slab in one launch, check it, and ship afterwards.)
 // The physical border of the global array is realised in the ghost planes: Fill -> constant planes,
 // Wrap -> ring neighbours, Edge/Reflect/Continue -> copies of the rank's own planes (handleBorderIndex
 // is per-dimension, Core/Index/Internal.hs:653-658, so a resolved ghost plane is an ordinary plane).
@@ -247,8 +250,6 @@ __global__ void fill_plane_kernel(unsigned char *dst, size_t n_elems, int esize,
 
 static int exchange(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, char *buf, cudaStream_t stream) {
   ShardState *S = c->shard;
-  static const bool skip = getenv("MASSIV_B200_NO_EXCHANGE") != nullptr;  // timing experiments only: results are wrong
-  if (skip) return MB_OK;
   if (sp.recv_lower_from < 0 && sp.recv_upper_from < 0 && sp.send_first_to < 0 && sp.send_last_to < 0) return MB_OK;
   NcclApi &api = nccl();
   char *first = buf + (size_t)g.lo * g.plane_bytes;                       // my first planes -> lower rank's upper ghost
@@ -662,8 +663,7 @@ static int iterate_sharded_locked(Ctx *c, const mb_stencil_desc *desc, const int
     MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_b, 0));
   }
 
-  const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0 ||
-                     getenv("MASSIV_B200_FORCE_SPLIT") != nullptr;  // experiment knob: peel boundary planes even when alone
+  const bool talks = sp.recv_lower_from >= 0 || sp.recv_upper_from >= 0 || sp.send_first_to >= 0 || sp.send_last_to >= 0;
   int cur = 0;
   for (int64_t s = 0; s < n_steps;) {
     const bool two = tb2_mode && n_steps - s >= 2;  // a fused pair of steps, or one step
