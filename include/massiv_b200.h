@@ -27,7 +27,10 @@
  *     contracted into FMA, in the reference's accumulation order: results
  *     are bit-identical to massiv's for finite and non-finite inputs (NaN payloads excepted).
  *     MB_FLAG_ASSUME_FINITE lets CONV/CORR/TAPS/MAG2 skip zero coefficients, which is
- *     bit-identical for finite inputs only (a skipped 0*Inf would have produced NaN).
+ *     bit-identical for finite inputs only (a skipped 0*Inf would have produced NaN).  The flag is
+ *     never needed for correctness or speed of the star-shaped 3x3x3 kernels: without it they skip
+ *     the zero taps optimistically, check on the device that no Inf / NaN was involved, and redo the
+ *     work with the strict 27-tap kernel otherwise.
  */
 #ifndef MASSIV_B200_H
 #define MASSIV_B200_H
@@ -156,8 +159,11 @@ const char *mb_last_error(mb_ctx *ctx);
 /* launch the context's kernels on an external cudaStream_t (NULL restores its own stream) */
 int mb_ctx_set_stream(mb_ctx *ctx, void *cuda_stream);
 int mb_sync(mb_ctx *ctx);
-/* tuning / test switches: "force_generic" (1 = always the generic kernel),
- * "life_bitpack" (0 = byte-wise Life kernels only) */
+/* tuning / test switches (none changes a result): "force_generic" (1 = always the generic kernel),
+ * "life_bitpack" (0 = byte-wise Life kernels only), "tile_min_elems" (arrays below this many output
+ * cells take the generic kernel), "no_tma" (stage tiles with cp.async), "no_known" (no compile-time
+ * coefficient kernels), "tb2" (0 = one step per pass when iterating), "no_optimistic" (1 = never skip
+ * zero taps without the caller's promise), "pipeline" (0 = serial copies in mb_run) */
 int mb_ctx_set_option(mb_ctx *ctx, const char *key, int64_t value);
 /* number of kernels of THIS library launched through the context so far */
 int64_t mb_launch_count(mb_ctx *ctx);
