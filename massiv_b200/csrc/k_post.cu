@@ -3,52 +3,9 @@
 // exactly specified IEEE-754 / two's-complement operation, so the mapped result stays bit-identical.
 // First version: an in-place elementwise pass over what the stencil kernel wrote (one extra read and
 // write of the OUTPUT per launch); fusing it into the kernels' store epilogues is the follow-up.
-#include "mb_arith.cuh"
-#include "mb_internal.h"
+#include "mb_post.cuh"
 
 namespace mb {
-
-struct PostParams {
-  int n;
-  int op[MB_MAX_POST];
-  unsigned long long operand[MB_MAX_POST];
-};
-
-template <typename T> __device__ __forceinline__ T post_one(int op, T x, T c) {
-  using A = Arith<T>;
-  if constexpr (A::is_float) {
-    switch (op) {
-      case MB_POST_NEGATE: return -x;                                    // negateFloat#: sign flip, also for 0 and NaN
-      case MB_POST_ABS: return x == T(0) ? T(0) : (x > T(0) ? x : -x);   // GHC.Float: abs (-0) = 0
-      case MB_POST_SIGNUM: return x > T(0) ? T(1) : (x < T(0) ? T(-1) : x);
-      case MB_POST_SQUARE: return A::mul(x, x);
-      case MB_POST_ADD: return A::add(x, c);
-      case MB_POST_SUB: return x - c;
-      case MB_POST_RSUB: return c - x;
-      case MB_POST_MUL: return A::mul(x, c);
-      case MB_POST_MIN: return x <= c ? x : c;
-      case MB_POST_MAX: return x <= c ? c : x;
-      case MB_POST_DIV: return A::div(x, c);
-      case MB_POST_RDIV: return A::div(c, x);
-      case MB_POST_RECIP: return A::div(T(1), x);
-      default: return A::sqrt(x);
-    }
-  } else {
-    using U = typename A::Acc;  // unsigned arithmetic wraps like Haskell's fixed-width integers
-    switch (op) {
-      case MB_POST_NEGATE: return (T)(U(0) - (U)x);
-      case MB_POST_ABS: return x >= T(0) ? x : (T)(U(0) - (U)x);
-      case MB_POST_SIGNUM: return x > T(0) ? T(1) : (x < T(0) ? (T)(U(0) - U(1)) : T(0));
-      case MB_POST_SQUARE: return (T)((U)x * (U)x);
-      case MB_POST_ADD: return (T)((U)x + (U)c);
-      case MB_POST_SUB: return (T)((U)x - (U)c);
-      case MB_POST_RSUB: return (T)((U)c - (U)x);
-      case MB_POST_MUL: return (T)((U)x * (U)c);
-      case MB_POST_MIN: return x <= c ? x : c;
-      default: return x <= c ? c : x;  // MB_POST_MAX (the Fractional ones are rejected at validation)
-    }
-  }
-}
 
 template <typename T>
 __global__ void __launch_bounds__(256) post_kernel(const PostParams P, T *__restrict__ data, size_t n) {
@@ -80,13 +37,7 @@ static int launch_post_t(Ctx *c, const PostParams &P, void *data, size_t n) {
 
 int launch_post(Ctx *c, const Plan &p, void *d_out, const OuterRange *range) {
   if (p.post.empty()) return MB_OK;
-  PostParams P;
-  std::memset(&P, 0, sizeof(P));
-  P.n = (int)p.post.size();
-  for (int i = 0; i < P.n; ++i) {
-    P.op[i] = p.post[i].op;
-    std::memcpy(&P.operand[i], p.post[i].operand, 8);
-  }
+  const PostParams P = make_post_params(p);
   int64_t plane = 1;
   for (int i = 1; i < p.rank; ++i) plane *= p.out_dims[i];
   int64_t o0 = 0, o1 = p.out_dims[0];

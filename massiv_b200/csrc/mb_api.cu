@@ -98,8 +98,9 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
 
 int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   if (dp.p.out_elems == 0) return MB_OK;
+  c->post_fused = false;
   int st = launch_family(c, dp, d_in, d_out, range);
-  if (st || dp.p.post.empty()) return st;
+  if (st || dp.p.post.empty() || c->post_fused) return st;
   // post-maps run as an in-place pass over what the stencil kernel just wrote (same stream)
   const char *family = c->last_kernel;
   st = launch_post(c, dp.p, d_out, range);

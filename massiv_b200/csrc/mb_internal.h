@@ -75,6 +75,7 @@ struct Ctx {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_a = nullptr, ev_b = nullptr;
   std::mutex mu;
   std::string err;
+  bool post_fused = false;   // set by a kernel family that applied the plan's post-maps in its store epilogue
   int64_t launches = 0;
   int64_t aux_launches = 0;  // of those: conditional follow-ups of the checked kernels, post-map passes, ghost fills
   const char *last_kernel = "none";
