@@ -39,7 +39,7 @@ template <typename T, int K, int XOFF> struct S2Cfg {
   static constexpr int SMEM = S * STAGE + TBUF + 64;
 };
 
-template <typename T, bool REV, int K, int XOFF>
+template <typename T, bool REV, int K, int XOFF, bool TMA>
 __global__ void __launch_bounds__(256, 2)
 sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const SepCoef<T, K> C2,
              const T *__restrict__ in, T *__restrict__ out) {
@@ -51,7 +51,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::S * C::STAGE + C::TBUF);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    if (P.use_tma) tma_prefetch_desc(&tmap);
+    if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < C::S; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
@@ -64,7 +64,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     ox0 = (t % P.tiles_x) * C::TW;
   };
   auto tma_ok = [&](int oy0, int ox0) -> bool {
-    if (!P.use_tma) return false;
+    if (!TMA) return false;
     if (P.zero_fill_ok) return true;
     const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x;
     const int th = min(C::TH, P.h - oy0), tw = min(C::TW, P.w - ox0);
@@ -85,7 +85,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     return by0 >= 0 && bx0 >= 0 && by0 + C::BH <= P.h && bx0 + C::BW <= P.w;
   };
   auto prefetch = [&](int i) {
-    if (P.use_tma) {
+    if (TMA) {
       if (tid == 0 && i < my_tiles) issue(i);
       return;
     }
@@ -117,7 +117,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     const int s = i % C::S;
     int oy0, ox0;
     tile_origin(i, oy0, ox0);
-    if (P.use_tma && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
+    if (TMA && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
     prefetch(i + C::S - 1);
     T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
     const bool by_tma = tma_ok(oy0, ox0);
@@ -125,11 +125,11 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     if (by_tma) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
-    } else if (!P.use_tma && box_inside(oy0, ox0)) {
+    } else if (!TMA && box_inside(oy0, ox0)) {
       cp_async_wait_group<C::S - 1>();
       __syncthreads();
     } else {
-      if (!P.use_tma) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
+      if (!TMA) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
       for (int e = tid; e < C::BW * C::BH; e += 256) {
         const int r = e / C::BW, c = e - r * C::BW;
         int gy = by0 + r, gx = bx0 + c;
@@ -247,9 +247,11 @@ static int launch_s2(Ctx *c, const Plan &p1, const Plan &p2, const void *d_in, v
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[2] = {(uint32_t)C::BH, (uint32_t)C::BW};
   P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p1.elem, p1.esize, 2, d_in, p1.in_dims, box)) ? 1 : 0;
-  auto kern = sep2d_kernel<T, REV, K, XOFF>;
-  static int occ_dev[64] = {0};
-  int &occ = occ_dev[c->device & 63];
+  auto kern_tma = sep2d_kernel<T, REV, K, XOFF, true>;
+  auto kern_cp = sep2d_kernel<T, REV, K, XOFF, false>;
+  auto kern = P.use_tma ? kern_tma : kern_cp;
+  static int occ_dev[64][2] = {{0}};
+  int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));

@@ -93,7 +93,10 @@ template <typename T, bool FIN> __device__ __forceinline__ T tap_known(T x, T ac
   return A::add(A::mul(x, T(kv)), acc);
 }
 
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false>
+// TMA: boxes come through the tensor map; false: the array has none (row pitch not a multiple of 16 bytes)
+// and boxes inside the array are staged with cp.async — a separate instantiation, so that the TMA
+// variant's register allocation is not disturbed (the 7x7 Float kernel sits at the 128-register limit).
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false, bool TMA = true>
 __global__ void __launch_bounds__(256, 2)
 tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const Coef<T, KH * KW> K,
               const T *__restrict__ in, T *__restrict__ out) {
@@ -105,7 +108,7 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::S * C::STAGE);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    if (P.use_tma) tma_prefetch_desc(&tmap);
+    if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < C::S; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
@@ -120,7 +123,7 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
   };
   // may tile i be fetched by TMA?  yes when out-of-range cells are never used or zero is the border
   auto tma_ok = [&](int oy0, int ox0) -> bool {
-    if (!P.use_tma) return false;
+    if (!TMA) return false;
     if (P.zero_fill_ok) return true;
     const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x;
     const int th = min(C::TH, P.y1 - oy0), tw = min(C::TW, P.out_w - ox0);
@@ -141,7 +144,7 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
     return by0 >= 0 && bx0 >= 0 && by0 + C::BH <= P.in_h && bx0 + C::BW <= P.in_w;
   };
   auto prefetch = [&](int i) {  // every thread
-    if (P.use_tma) {
+    if (TMA) {
       if (tid == 0 && i < my_tiles) issue(i);
       return;
     }
@@ -172,18 +175,18 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
     const int s = i % C::S;
     int oy0, ox0;
     tile_origin(i, oy0, ox0);
-    if (P.use_tma && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
+    if (TMA && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
     prefetch(i + C::S - 1);
     T *sm = reinterpret_cast<T *>(smem + s * C::STAGE);
     const bool by_tma = tma_ok(oy0, ox0);
     if (by_tma) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
-    } else if (!P.use_tma && sizeof(T) >= 4 && box_inside(oy0, ox0)) {
+    } else if (!TMA && sizeof(T) >= 4 && box_inside(oy0, ox0)) {
       cp_async_wait_group<C::S - 1>();  // this tile's group has landed (S - 1 younger ones may be in flight)
       __syncthreads();
     } else {
-      if (!P.use_tma) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
+      if (!TMA) cp_async_wait_group<C::S - 1>();  // keeps the group count in step
       // peeled edge path: every box cell through the border rule (Core/Index.hs:236-253)
       const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - XOFF;
       for (int e = tid; e < C::BW * C::BH; e += 256) {
@@ -314,9 +317,11 @@ static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[2] = {(uint32_t)C::BH, (uint32_t)C::BW};
   P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box)) ? 1 : 0;
-  auto kern = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN>;
-  static int occ_dev[64] = {0};  // per device: the smem opt-in is a per-device function attribute
-  int &occ = occ_dev[c->device & 63];
+  auto kern_tma = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN, true>;
+  auto kern_cp = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN, false>;
+  auto kern = P.use_tma ? kern_tma : kern_cp;
+  static int occ_dev[64][2] = {{0}};  // per device: the smem opt-in is a per-device function attribute
+  int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
