@@ -53,8 +53,45 @@ static int geometry() {
   return failures;
 }
 
+// every Int case of tests/golden/massiv_golden.json (the reference's StencilSpec / doctest vectors)
+struct GoldenCase {
+  const char *name;
+  mb_kind kind;
+  Ix in_dims;
+  std::vector<int64_t> input;
+  Ix expect_dims;
+  std::vector<int64_t> expect;
+  Ix size;
+  int has_center;
+  Ix center, pad_lo, pad_hi;
+  mb_border border;
+  int64_t fill;
+  Ix stride;
+  std::vector<int64_t> coeffs, taps;
+};
+static const GoldenCase kGolden[] = {
+#include "golden/golden_i64.inc"
+};
+
+static void golden(const Device &dev) {
+  for (const GoldenCase &c : kGolden) {
+    Stencil<int64_t> st;
+    st.kind = c.kind; st.size = c.size; st.coeffs = c.coeffs; st.tap_offsets = c.taps;
+    if (c.has_center) st.center = c.center;
+    else
+      for (int64_t n : c.size)  // stencilCenter of the built-in constructors
+        st.center.push_back(c.kind == MB_CONV ? n - 1 - n / 2 : (c.kind == MB_CORR ? n / 2 : 0));
+    const Array<int64_t> arr(Sz(c.in_dims), c.input);
+    const Border<int64_t> b{c.border, c.fill};
+    const DW<int64_t> dw = c.pad_lo.empty() ? mapStencil(b, st, arr) : applyStencil(Padding<int64_t>{c.pad_lo, c.pad_hi, b}, st, arr);
+    const Array<int64_t> got = c.stride.empty() ? compute(dev, dw) : computeWithStride(dev, c.stride, dw);
+    CHECK((got.sz == Sz(c.expect_dims) && got.elems == c.expect), c.name);
+  }
+}
+
 static int gpu() {
   Device dev(0);
+  golden(dev);
   {  // StencilSpec.hs:227, 237: conv / corr of [1,2,3] over [1..5], Fill 0
     const Array<int64_t> ys = iota<int64_t>(Sz{5}, 1), k(Sz{3}, {1, 2, 3});
     const auto conv = compute(dev, mapStencil(Border<int64_t>::Fill(0), makeConvolutionStencilFromKernel(k), ys));

@@ -15,7 +15,7 @@ def _build():
     _abi.lib()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     libdir = os.path.join(ROOT, "massiv_b200")
-    cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx_harness.cpp"),
+    cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "cxx_harness.cpp"),
            "-o", EXE, "-L", libdir, "-l:libmassiv_b200.so", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
