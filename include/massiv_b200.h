@@ -163,7 +163,8 @@ int mb_sync(mb_ctx *ctx);
  * "life_bitpack" (0 = byte-wise Life kernels only), "tile_min_elems" (arrays below this many output
  * cells take the generic kernel), "no_tma" (stage tiles with cp.async), "no_known" (no compile-time
  * coefficient kernels), "tb2" (0 = one step per pass when iterating), "no_optimistic" (1 = never skip
- * zero taps without the caller's promise), "pipeline" (0 = serial copies in mb_run) */
+ * zero taps without the caller's promise), "pipeline" (0 = serial copies in mb_run), "no_p2p" (1 = sharded
+ * iteration moves halo planes with ncclSend/ncclRecv; must be set alike on every rank) */
 int mb_ctx_set_option(mb_ctx *ctx, const char *key, int64_t value);
 /* number of kernels of THIS library launched through the context so far */
 int64_t mb_launch_count(mb_ctx *ctx);
@@ -217,9 +218,12 @@ int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, co
 
 /* ---- slab-sharded iteration across the GPUs of one box (one process per GPU) ---------------- */
 /* The global array is split along dims[0] into contiguous slabs, rank r owning planes
- * [r*N/R, (r+1)*N/R).  Every step exchanges `halo` ghost planes with rank±1 (ncclSend/ncclRecv on
- * a second stream, overlapped with the interior kernel).  The rendezvous itself (who is who, the
- * unique id broadcast) is the host's job — torch.distributed in this repo. */
+ * [r*N/R, (r+1)*N/R).  Every round (one step, or two fused steps for star-shaped 3-D kernels under
+ * Fill 0) exchanges the ghost planes with rank±1: copy-engine peer copies over NVLink into IPC-mapped
+ * staging areas with counter hand-shakes in device memory (no SM involved), or — when peer memory cannot
+ * be mapped, or under option "no_p2p" / MASSIV_B200_NO_P2P — ncclSend/ncclRecv on a second stream.  NCCL
+ * is always the rendezvous for the IPC handles.  The process rendezvous itself (who is who, the unique id
+ * broadcast) is the host's job — torch.distributed in this repo. */
 #define MB_NCCL_ID_BYTES 128
 #define MB_MAX_HALO 8
 #define MB_GHOST_FILL (-1)   /* ghost plane is the Fill element (physical border)            */
@@ -235,7 +239,8 @@ typedef struct mb_shard_plan {
   int32_t send_last_to;              /* rank that needs my last halo_lo planes (its lower ghost), or -1  */
   int64_t ghost_lo_src[MB_MAX_HALO]; /* per ghost plane: >= 0 own local plane to copy (Edge /   */
   int64_t ghost_hi_src[MB_MAX_HALO]; /* Reflect / Continue / 1-rank Wrap), MB_GHOST_FILL, or MB_GHOST_REMOTE */
-  int64_t step_halo_lo, step_halo_hi; /* planes ONE step reads beyond the slab (centre, size-1-centre);
+  int64_t step_halo_lo, step_halo_hi; /* planes ONE step reads beyond the slab (pad_lo[0], pad_hi[0]: for
+                                         mapStencil these are centre and size-1-centre);
                                          halo_* is twice that for stencils iterated two steps per
                                          pass (temporal blocking) */
 } mb_shard_plan;
@@ -261,6 +266,11 @@ int mb_iterate_sharded(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *
                        const int64_t *local_dims, const void *host_in, void *host_out, int64_t n_steps);
 
 /* ---- device self-test (tests only) ----------------------------------------------------------- */
+/* bitwise comparison of two device buffers: *mismatches = number of differing 8-byte words (bytes in an
+ * unaligned tail), *first_offset = byte offset of the first one (UINT64_MAX when equal).  Used by the
+ * full-size verification in bench.py and by the tests; blocks until the answer is known. */
+int mb_compare_dev(mb_ctx *ctx, const void *dev_a, const void *dev_b, size_t bytes, uint64_t *mismatches,
+                   uint64_t *first_offset);
 /* compares the three-operation exact quotient avgStencil uses with the IEEE divide on `count`
  * random / adversarial bit patterns of element type MB_F32 or MB_F64; *mismatches must be 0 */
 int mb_selftest_div(mb_ctx *ctx, int elem, int64_t n, uint64_t count, uint64_t seed,

@@ -32,7 +32,7 @@ SYMBOLS = [
     "mb_elem_size", "mb_out_dims", "mb_border_index", "mb_buf_alloc", "mb_buf_free", "mb_upload",
     "mb_download", "mb_host_alloc", "mb_host_free", "mb_run", "mb_run_dev", "mb_run_sep2_dev",
     "mb_run_sep2", "mb_iterate_dev", "mb_iterate", "mb_nccl_unique_id", "mb_shard_init",
-    "mb_shard_halo", "mb_shard_plan_make", "mb_iterate_sharded_dev", "mb_iterate_sharded", "mb_shard_transport", "mb_timer_start", "mb_timer_stop", "mb_selftest_div",
+    "mb_shard_halo", "mb_shard_plan_make", "mb_iterate_sharded_dev", "mb_iterate_sharded", "mb_shard_transport", "mb_timer_start", "mb_timer_stop", "mb_selftest_div", "mb_compare_dev",
 ]
 
 
@@ -153,6 +153,7 @@ def lib() -> C.CDLL:
     L.mb_shard_transport.argtypes = [vp]
     L.mb_selftest_div.argtypes = [vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64)]
+    L.mb_compare_dev.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.mb_timer_start.argtypes = [vp]
     L.mb_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(256, 1) life_bits_kernel(const LifeBitsParams 
 int life_iterate(Ctx *c, const DevPlan &dp, void *d_a, void *d_b, int64_t n_steps, void **result) {
   const Plan &p = dp.p;
   if (!c->life_bitpack || !life_byte_ok(p, d_a, d_b) || n_steps < 3) return -1;
+  if (n_steps - 1 > (int64_t)0x7fffffff) return -1;  // the kernel counts generations in an int: single steps instead
   const int h = (int)p.in_dims[0], w = (int)p.in_dims[1];
   bool fill0 = p.border == MB_FILL && p.fill[0] == 0;
   if (p.border != MB_WRAP && !fill0) return -1;

@@ -54,9 +54,56 @@ __global__ void div_selftest_kernel(DivCount dc, unsigned long long count, unsig
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// bitwise comparison of two device buffers (tests / bench verification): counts differing bytes' words and
+// reports the first differing byte offset
+__global__ void compare_kernel(const unsigned char *a, const unsigned char *b, unsigned long long bytes, bool words,
+                               unsigned long long *count, unsigned long long *first) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long bad = 0, where = ~0ull;
+  if (words) {
+    const unsigned long long n = bytes / 8;
+    const unsigned long long *x = reinterpret_cast<const unsigned long long *>(a), *y = reinterpret_cast<const unsigned long long *>(b);
+    for (unsigned long long i = tid; i < n; i += stride)
+      if (x[i] != y[i]) { ++bad; if (where == ~0ull) where = i * 8; }
+    for (unsigned long long i = n * 8 + tid; i < bytes; i += stride)
+      if (a[i] != b[i]) { ++bad; if (where == ~0ull) where = i; }
+  } else {
+    for (unsigned long long i = tid; i < bytes; i += stride)
+      if (a[i] != b[i]) { ++bad; if (where == ~0ull) where = i; }
+  }
+  if (bad) { atomicAdd(count, bad); atomicMin(first, where); }
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int mb_compare_dev(mb_ctx *h, const void *dev_a, const void *dev_b, size_t bytes, uint64_t *mismatches,
+                              uint64_t *first_offset) {
+  if (!h || !mismatches) return MB_ERR_INVALID_DESC;
+  Ctx *c = &h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MB_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long *d = nullptr;
+  MB_CUDA(c, cudaMalloc(&d, 16));
+  const unsigned long long init[2] = {0ull, ~0ull};
+  MB_CUDA(c, cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, c->stream));
+  if (bytes) {
+    const bool words = ((uintptr_t)dev_a % 8 == 0) && ((uintptr_t)dev_b % 8 == 0);
+    compare_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((const unsigned char *)dev_a, (const unsigned char *)dev_b,
+                                                          (unsigned long long)bytes, words, d, d + 1);
+    c->launches++;
+    c->aux_launches++;
+  }
+  unsigned long long hres[2] = {0, 0};
+  MB_CUDA(c, cudaMemcpyAsync(hres, d, 16, cudaMemcpyDeviceToHost, c->stream));
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  MB_CUDA(c, cudaFree(d));
+  *mismatches = hres[0];
+  if (first_offset) *first_offset = hres[1];
+  return MB_OK;
+}
 
 extern "C" int mb_selftest_div(mb_ctx *h, int elem, int64_t n, uint64_t count, uint64_t seed, uint64_t *mismatches,
                                uint64_t *first_bad_bits) {

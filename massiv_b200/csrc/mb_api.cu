@@ -65,8 +65,7 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
   const Plan &q = dp->p;
   if (!q.tap_off.empty()) {
     MB_CUDA(c, cudaMalloc(&dp->d_taps, q.tap_off.size() * sizeof(int32_t)));
-    MB_CUDA(c, cudaMemcpyAsync(dp->d_taps, q.tap_off.data(), q.tap_off.size() * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(c, cudaMemcpy(dp->d_taps, q.tap_off.data(), q.tap_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   if (!q.tap_off.empty()) {
     std::vector<int64_t> lin((size_t)q.ntaps);
@@ -80,13 +79,14 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
   }
   if (!q.c1.empty()) {
     MB_CUDA(c, cudaMalloc(&dp->d_c1, q.c1.size()));
-    MB_CUDA(c, cudaMemcpyAsync(dp->d_c1, q.c1.data(), q.c1.size(), cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(c, cudaMemcpy(dp->d_c1, q.c1.data(), q.c1.size(), cudaMemcpyHostToDevice));
   }
   if (!q.c2.empty()) {
     MB_CUDA(c, cudaMalloc(&dp->d_c2, q.c2.size()));
-    MB_CUDA(c, cudaMemcpyAsync(dp->d_c2, q.c2.data(), q.c2.size(), cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(c, cudaMemcpy(dp->d_c2, q.c2.data(), q.c2.size(), cudaMemcpyHostToDevice));
   }
-  // pageable-source async copies are staged before returning, so q's vectors may move freely
+  // the tables are uploaded synchronously: a cached plan may later be launched on another stream
+  // (mb_ctx_set_stream) with no ordering against the stream that was current here
   c->plans[key] = dp;
   *out = dp;
   return MB_OK;
@@ -296,11 +296,25 @@ int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out
   MB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
   MB_CUDA(c, cudaStreamWaitEvent(c->out_stream, c->ev_a, 0));
   auto in_begin = [&](int j) { return D * j / nch; };
+  // once anything has been queued, an error may not return while copies into the scratch buffers or into the
+  // caller's host_out are still in flight (the caller may free or reuse them): drain the three streams first
+  auto bail = [&](int st) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->out_stream);
+    cudaGetLastError();
+    return st;
+  };
+#define MB_PIPE(expr)                                      \
+  do {                                                     \
+    int _ps = ::mb::check_cuda(c, (expr), #expr);          \
+    if (_ps) return bail(_ps);                             \
+  } while (0)
   for (int j = 0; j < nch; ++j) {
     const int64_t a = in_begin(j), b = in_begin(j + 1);
-    MB_CUDA(c, cudaMemcpyAsync((char *)d_in + a * in_plane, (const char *)host_in + a * in_plane, (size_t)(b - a) * in_plane,
+    MB_PIPE(cudaMemcpyAsync((char *)d_in + a * in_plane, (const char *)host_in + a * in_plane, (size_t)(b - a) * in_plane,
                                cudaMemcpyHostToDevice, c->comm_stream));
-    MB_CUDA(c, cudaEventRecord(c->pipe_events[j], c->comm_stream));
+    MB_PIPE(cudaEventRecord(c->pipe_events[j], c->comm_stream));
   }
   for (int k = 0; k < nch; ++k) {
     const OuterRange r{OD * k / nch, OD * (k + 1) / nch};
@@ -321,14 +335,15 @@ int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out
         while (j_hi + 1 < nch && in_begin(j_hi + 1) <= far) ++j_hi;
       }
     }
-    MB_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_events[j_hi], 0));
+    MB_PIPE(cudaStreamWaitEvent(c->stream, c->pipe_events[j_hi], 0));
     int st = launch_plan(c, dp, d_in, d_out, &r);
-    if (st) return st;
-    MB_CUDA(c, cudaEventRecord(c->pipe_events[16 + k], c->stream));
-    MB_CUDA(c, cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
-    MB_CUDA(c, cudaMemcpyAsync((char *)host_out + r.o0 * out_plane, (const char *)d_out + r.o0 * out_plane,
+    if (st) return bail(st);
+    MB_PIPE(cudaEventRecord(c->pipe_events[16 + k], c->stream));
+    MB_PIPE(cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
+    MB_PIPE(cudaMemcpyAsync((char *)host_out + r.o0 * out_plane, (const char *)d_out + r.o0 * out_plane,
                                (size_t)(r.o1 - r.o0) * out_plane, cudaMemcpyDeviceToHost, c->out_stream));
   }
+#undef MB_PIPE
   (void)ob;
   MB_CUDA(c, cudaStreamSynchronize(c->out_stream));
   MB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -441,6 +456,8 @@ const char *mb_last_error(mb_ctx *h) { return h ? h->c.err.c_str() : "null conte
 int mb_ctx_set_stream(mb_ctx *h, void *s) {
   Guard g(h);
   if (g.st) return g.st;
+  // work queued on the old stream (scratch reuse, frees) is not ordered against the new one: drain it
+  MB_CUDA(g.c, cudaStreamSynchronize(g.c->stream));
   g.c->stream = s ? (cudaStream_t)s : g.c->own_stream;
   return MB_OK;
 }
@@ -457,6 +474,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "no_tma") g.c->no_tma = (int)value;
   else if (k == "no_known") g.c->no_known = (int)value;
   else if (k == "tb2") g.c->tb2 = (int)value;
+  else if (k == "no_p2p") g.c->no_p2p = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }

@@ -150,12 +150,15 @@ static int ghost_sources(const mb_stencil_desc *d, const Plan &p, int64_t N, int
   std::memset(out, 0, sizeof(*out));
   out->first_plane = (int64_t)rank * N / n_ranks;
   out->local_planes = (int64_t)(rank + 1) * N / n_ranks - out->first_plane;
-  out->step_halo_lo = p.center[0];
-  out->step_halo_hi = p.geom[0] - 1 - p.center[0];
-  if (out->step_halo_hi < 0) out->step_halo_hi = 0;
+  // the planes ONE application reads below / above the slab.  Output plane o evaluates the stencil at source
+  // plane o + (centre - pad_lo) (Array/Stencil.hs:200), so its window covers o - pad_lo .. o + pad_hi for a
+  // size-preserving descriptor (pad_lo + pad_hi = size - 1): the PADDING is the halo.  For mapStencil
+  // (pad_lo = centre) this is the familiar centre / size-1-centre.
+  out->step_halo_lo = p.pad_lo[0];
+  out->step_halo_hi = p.pad_hi[0];
   // temporally blocked stencils advance two steps per exchange and therefore keep two steps' worth
   // of ghost planes
-  const int64_t depth = tb2_desc_eligible(d) ? 2 : 1;
+  const int64_t depth = (tb2_desc_eligible(d) && p.pad_lo[0] == 1 && p.pad_hi[0] == 1) ? 2 : 1;
   out->halo_lo = out->step_halo_lo * depth;
   out->halo_hi = out->step_halo_hi * depth;
   if (out->halo_lo > MB_MAX_HALO || out->halo_hi > MB_MAX_HALO) return bad(MB_ERR_UNSUPPORTED, "halo deeper than MB_MAX_HALO planes");
@@ -315,8 +318,12 @@ static inline size_t stage_slot(const SlabGeom &g, int p, int side) {
 static int setup_p2p(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, P2P *out) {
   ShardState *S = c->shard;
   out->on = false;
-  if (S->n < 2 || getenv("MASSIV_B200_NO_P2P")) return MB_OK;
+  if (S->n < 2) return MB_OK;
   NcclApi &api = nccl();
+  // A rank that does not want (MASSIV_B200_NO_P2P / option "no_p2p") or cannot use peer memory still takes
+  // part in the handle exchange and the consensus below, saying "no": whether peer memory is used is decided
+  // from state only one process knows, and a rank that simply left would leave its neighbours waiting.
+  const bool unwanted = c->no_p2p || getenv("MASSIV_B200_NO_P2P") != nullptr;
   if (!S->p2p_tried) {
     S->p2p_tried = true;
     void *fp = nullptr;
@@ -329,16 +336,15 @@ static int setup_p2p(Ctx *c, const mb_shard_plan &sp, const SlabGeom &g, P2P *ou
     // allocations of 2 MiB and more are blocks of their own, so their IPC handles are unambiguous
     ok = ok && cudaMalloc(&S->flags, (size_t)2 << 20) == cudaSuccess;
     ok = ok && cudaMemset(S->flags, 0, (size_t)2 << 20) == cudaSuccess;
-    ok = ok && cudaMalloc(&S->stage, 3 * sizeof(IpcInfo)) == cudaSuccess;
     S->p2p_ok = ok;
     if (!ok) p2p_note(S, "cannot allocate the counter block");
     cudaGetLastError();
   }
-  if (!S->stage) return MB_OK;  // cannot even say "no": the tiny allocation fails on every rank alike or not at all
+  if (!S->stage) return fail(c, MB_ERR_OOM, "internal: the handle-exchange scratch was not allocated by mb_shard_init");
   // 1. my side: staging area, counters set to the communicator's round number, magic words
   IpcInfo mine;
   std::memset(&mine, 0, sizeof(mine));
-  mine.ok = S->p2p_ok ? 1 : 0;
+  mine.ok = (S->p2p_ok && !unwanted) ? 1 : 0;
   const size_t need = STAGE_HEADER + 2 * (size_t)(g.lo + g.hi) * g.plane_bytes;
   if (mine.ok && S->xstage_bytes < need) {
     if (S->xstage) S->retired.push_back(S->xstage);
@@ -540,6 +546,9 @@ int mb_shard_init(mb_ctx *h, int n_ranks, int rank, const uint8_t *id) {
   ncclUniqueId u;
   std::memcpy(&u, id, sizeof(u));
   MB_NCCL(c, api.CommInitRank(&c->shard->comm, n_ranks, u, rank));
+  // scratch for the IPC-handle exchange of the peer-memory path: allocated here, where a failure is reported to
+  // the caller on every rank alike, so that setup_p2p can always take part in the exchange
+  MB_CUDA(c, cudaMalloc(&c->shard->stage, 3 * sizeof(IpcInfo)));
   return MB_OK;
 }
 

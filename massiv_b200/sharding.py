@@ -5,7 +5,8 @@ drivers use it:
 
 * :func:`iterate_sharded` — the product path: rendezvous over ``torch.distributed`` (only to hand
   the NCCL unique id around), then ``mb_iterate_sharded_dev`` which runs the whole loop natively
-  (boundary planes -> ncclSend/ncclRecv on a second stream -> interior planes -> join).
+  (boundary planes -> halo push: copy-engine peer copies into the neighbours' IPC-mapped staging areas, or
+  ncclSend/ncclRecv on a second stream when peer memory is unavailable -> interior planes -> join).
 * :func:`iterate_sharded_hostcheck` — the same choreography spelled out in Python over any
   ``torch.distributed`` backend (gloo on CPU) with a caller-supplied single-slab compute function.
   It exists so the multi-rank host logic (partition, ghost sources at the physical border, exchange
@@ -64,7 +65,9 @@ def iterate_sharded(n: int, border: Border, stencil: Stencil, local: DeviceArray
     `init_comm` must have been called on the device."""
     dev = local.dev
     L = dev._L
-    desc = mapStencil(border, stencil, local).desc()
+    from .stencil import Padding, applyStencil
+    dw = applyStencil(border, stencil._resolved(local.ndim), local) if isinstance(border, Padding) else mapStencil(border, stencil, local)
+    desc = dw.desc()
     lo, hi = C.c_int64(), C.c_int64()
     dev.check(L.mb_shard_halo(C.byref(desc), C.byref(lo), C.byref(hi)))
     planes = local.shape[0] + lo.value + hi.value

@@ -588,8 +588,9 @@ def computeInto(out: DeviceArray, dw: DW) -> DeviceArray:
 
 def iterateStencil(n: int, border: Border, stencil: Stencil, arr: Array, device: Optional[Device] = None) -> Array:
     """``iterateUntil (\\k _ _ -> k >= n-1) (\\_ -> mapStencil border stencil) arr``
-    (Manifest/Internal.hs:331-397): n >= 1 applications, double-buffered."""
-    dw = mapStencil(border, stencil, arr)
+    (Manifest/Internal.hs:331-397): n >= 1 applications, double-buffered.  `border` may also be a size-preserving
+    :class:`Padding` (``applyStencil padding stencil`` as the step)."""
+    dw = applyStencil(border, stencil._resolved(arr.ndim), arr) if isinstance(border, Padding) else mapStencil(border, stencil, arr)
     dev = _device_of(dw, device)
     d = dw.desc()
     L = dev._L

@@ -46,6 +46,11 @@ CASES = {
     "life-wrap": dict(shape=(16, 12), dtype=np.uint8, border=("wrap",), kind="life", size=(3, 3)),
     "sum5-reflect": dict(shape=(17, 9), dtype=np.int64, border=("reflect",), kind="sum", size=(5, 2)),
     "corr4-edge": dict(shape=(19, 8), dtype=np.float64, border=("edge",), kind="corr", size=(4, 3)),
+    # size-preserving descriptors that are NOT mapStencil-shaped along dim 0 (pad_lo != centre): the halo is the
+    # padding, not centre / size-1-centre.  sumStencil (3,1) with Padding (2,0) (0,0): window = planes o-2 .. o
+    "sum3-shifted-fill": dict(shape=(13, 5), dtype=np.int64, border=("fill", 0), kind="sum", size=(3, 1), pad=((2, 0), (0, 0))),
+    "sum3-shifted-wrap": dict(shape=(12, 5), dtype=np.int64, border=("wrap",), kind="sum", size=(3, 1), pad=((1, 0), (1, 0))),
+    "corr3-shifted-reflect": dict(shape=(14, 6), dtype=np.float64, border=("reflect",), kind="corr", size=(3, 3), pad=((0, 1), (2, 1))),
 }
 
 
@@ -72,7 +77,15 @@ def make_case(name):
     st = M.Stencil(c["kind"], tuple(c["size"]), None, None if coeffs is None else coeffs.reshape(c["size"]), flags=flags)
     okw = dict(size=c["size"], border=b[0], fill=b[1] if b[0] == "fill" else 0,
                coeffs=None if coeffs is None else coeffs.tolist())
+    if "pad" in c:
+        okw["pad_lo"], okw["pad_hi"] = c["pad"]
     return arr, border, st, c["kind"], okw
+
+
+def make_dw(border, st, arr, okw):
+    if "pad_lo" in okw:
+        return M.applyStencil(M.Padding(tuple(okw["pad_lo"]), tuple(okw["pad_hi"]), border), st, arr)
+    return M.mapStencil(border, st, arr)
 
 
 def _worker(rank, world, port, names, steps, q):
@@ -84,7 +97,7 @@ def _worker(rank, world, port, names, steps, q):
     try:
         for name in names:
             arr, border, st, kind, okw = make_case(name)
-            desc = M.mapStencil(border, st, arr).desc()
+            desc = make_dw(border, st, arr, okw).desc()
             sp = sharding.shard_plan(desc, arr.shape, world, rank)
             local = arr[sp.first_plane:sp.first_plane + sp.local_planes]
             out = sharding.iterate_sharded_hostcheck(steps, desc, local, arr.shape, dist, oracle_compute,
@@ -132,7 +145,7 @@ def test_sharded_choreography_matches_global_oracle(world):
 def test_single_rank_hostcheck_covers_every_border():
     for name in sorted(CASES):
         arr, border, st, kind, okw = make_case(name)
-        desc = M.mapStencil(border, st, arr).desc()
+        desc = make_dw(border, st, arr, okw).desc()
         got = sharding.iterate_sharded_hostcheck(2, desc, arr, arr.shape, None, oracle_compute, fill_value=okw["fill"])
         assert got.tobytes() == O.iterate(kind, arr, 2, **okw).tobytes(), name
 
@@ -182,6 +195,11 @@ def test_shard_plan_partition_and_ghost_sources():
     assert sharding.shard_plan(M.mapStencil(M.Fill(0.0), M.makeConvolutionStencilFromKernel(ks), arr).desc(), arr.shape, 2, 0).halo_lo == 2
     assert sharding.shard_plan(M.mapStencil(M.Fill(1.0), M.makeConvolutionStencilFromKernel(ks).assumeFinite(), arr).desc(),
                                arr.shape, 2, 0).halo_lo == 1   # non-zero Fill: single steps
+    # the halo is the padding: a shifted size-preserving window reads two planes below and none above
+    dsh = M.applyStencil(M.Padding((2, 0, 0), (0, 1, 1), M.Fill(0.0)), M.sumStencil(M.Sz(3, 2, 2)), arr).desc()
+    psh = sharding.shard_plan(dsh, arr.shape, 2, 1)
+    assert (psh.halo_lo, psh.halo_hi, psh.step_halo_lo, psh.step_halo_hi) == (2, 0, 2, 0)
+    assert (psh.recv_lower_from, psh.recv_upper_from) == (0, -1)
     # slabs thinner than the halo are refused, as is a shape-changing stencil
     with pytest.raises(M.MassivB200Error):
         sharding.shard_plan(d, arr.shape, 8, 0)
