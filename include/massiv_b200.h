@@ -81,8 +81,17 @@ typedef enum mb_kind {
    * (size is 1 elsewhere), centre 0, coeffs[0] = dx.  g_i is the i-th sample along that dimension. */
   MB_INT_MIDPOINT,  /* size k:    dx * (((0 + g_0) + g_1) + ... + g_{k-1})              Integral.hs:54-66   */
   MB_INT_TRAPEZOID, /* size n+1:  (dx/2) * ((g_0 + 2*g_1 + ... + 2*g_{n-1}) + g_n)       Integral.hs:75-90   */
-  MB_INT_SIMPSON    /* size n+1, n even >= 2: (dx/3) * acc, acc = ((acc + g_i) + 4*g_{i+1}) + g_{i+2}
+  MB_INT_SIMPSON,   /* size n+1, n even >= 2: (dx/3) * acc, acc = ((acc + g_i) + 4*g_{i+1}) + g_{i+2}
                        over i = 0, 2, .., n-2                                           Integral.hs:99-118  */
+  /* A stencil EXPRESSION: the Applicative / Num / Fractional / Floating instances of Stencil
+   * (Array/Stencil/Internal.hs:83-174).  `terms` are sub-stencils of the kinds above (ID .. TAPS), every one
+   * evaluated at the same absolute source index; `program` combines their values point-wise in postfix order
+   * (liftA2 (+|-|*|/), fmap f, pure c).  size / center of the descriptor are the union the reference computes:
+   * centre = max of the terms' centres, size = centre + max (size_t - centre_t) (unionStencilCenters / Sizes,
+   * Internal.hs:83-90); they are validated.  Example: the closure-form Sobel operator of the reference's own
+   * benchmark, sqrt (sX * sX + sY * sY) (massiv-bench/src/Data/Massiv/Bench/Sobel.hs:15-44), is two TAPS terms
+   * and the program  T0 T0 MUL T1 T1 MUL ADD SQRT. */
+  MB_EXPR
 } mb_kind;
 
 /* Border (Core/Index.hs:159-195) resolved by handleBorderIndex (Core/Index.hs:236-253) */
@@ -116,6 +125,43 @@ typedef struct mb_post_op {
   uint8_t operand[8]; /* c in the element type (native-endian, first sizeof(elem) bytes) */
 } mb_post_op;
 
+/* One sub-stencil of an MB_EXPR descriptor: the fields of mb_stencil_desc that define WHICH values are combined
+ * (kind, size, centre, kernel / tap list); element type, rank, border, padding and stride are the expression's. */
+typedef struct mb_term {
+  int32_t kind;                  /* mb_kind: MB_ID, MB_SUM, MB_PRODUCT, MB_AVG, MB_MAX, MB_MIN, MB_CONV, MB_CORR, MB_TAPS */
+  int32_t reserved;
+  int64_t size[MB_MAX_RANK];
+  int64_t center[MB_MAX_RANK];   /* stencilCenter of the term on its own (validated like a descriptor's)      */
+  const void *coeffs;            /* CONV/CORR: prod(size) elements; TAPS: ntaps                               */
+  int64_t ntaps;                 /* TAPS                                                                      */
+  const int64_t *tap_offsets;    /* TAPS: ntaps*rank                                                          */
+} mb_term;
+/* Postfix program over a value stack (depth <= MB_MAX_STACK).  Binary operators pop b then a and push a OP b. */
+typedef enum mb_xop {
+  MB_X_TERM = 1,  /* push the value of terms[arg]                                         */
+  MB_X_CONST,     /* push `operand`: pure c / fromInteger / fromRational                  */
+  MB_X_ADD,       /* liftA2 (+)      Internal.hs:115                                      */
+  MB_X_SUB,       /* liftA2 (-)                                                           */
+  MB_X_MUL,       /* liftA2 (*)                                                           */
+  MB_X_DIV,       /* liftA2 (/)      Fractional e                 Internal.hs:131         */
+  MB_X_MIN,       /* liftA2 min: min a b = if a <= b then a else b (GHC.Classes default)  */
+  MB_X_MAX,       /* liftA2 max: max a b = if a <= b then b else a                        */
+  MB_X_NEGATE,    /* fmap negate; the unary operators follow mb_post                      */
+  MB_X_ABS,
+  MB_X_SIGNUM,
+  MB_X_SQUARE,    /* fmap (^2): x * x                                                     */
+  MB_X_RECIP,     /* fmap recip: 1 / x        Fractional e                                */
+  MB_X_SQRT       /* fmap sqrt                Floating e                                  */
+} mb_xop;
+typedef struct mb_xins {
+  int32_t op;         /* mb_xop */
+  int32_t arg;        /* MB_X_TERM: index into terms */
+  uint8_t operand[8]; /* MB_X_CONST: c in the element type */
+} mb_xins;
+#define MB_MAX_TERMS 8
+#define MB_MAX_PROGRAM 32
+#define MB_MAX_STACK 8
+
 #define MB_FLAG_MAG2_CORR 1u     /* MAG2 sub-stencils are correlations                         */
 #define MB_FLAG_ASSUME_FINITE 2u /* inputs are finite: zero coefficients may be skipped        */
 
@@ -144,6 +190,11 @@ typedef struct mb_stencil_desc {
   uint32_t flags;
   uint32_t n_post;               /* number of post-maps, <= MB_MAX_POST                       */
   const mb_post_op *post;        /* applied in order to every result                          */
+  /* MB_EXPR only (zero / NULL otherwise) */
+  uint32_t n_terms;              /* <= MB_MAX_TERMS                                            */
+  uint32_t n_program;            /* <= MB_MAX_PROGRAM                                          */
+  const mb_term *terms;
+  const mb_xins *program;
 } mb_stencil_desc;
 
 typedef struct mb_ctx mb_ctx;

@@ -25,7 +25,9 @@ SOURCES = ["mb_plan.cpp", "mb_api.cu", "k_generic.cu", "k_tile2d.cu", "k_vol3d.c
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: belt and braces — the kernels already use explicit *_rn intrinsics, which nvcc
 # never contracts; explicit fma() calls (exact-division helper) are unaffected by the flag.
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+# (tuning variants are built without -lineinfo, MB_NO_LINEINFO=1: the libraries are a third smaller and the GPU box's
+# snapshot has a size limit)
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17"] + ([] if os.environ.get("MB_NO_LINEINFO") else ["-lineinfo"]) + ["-fmad=false",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--expt-relaxed-constexpr",
          "-I", os.path.join(ROOT, "include")] + os.environ.get("MB_NVCC_EXTRA", "").split()
 

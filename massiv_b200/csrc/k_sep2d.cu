@@ -93,11 +93,9 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
       int oy0, ox0;
       tile_origin(i, oy0, ox0);
       if (box_inside(oy0, ox0)) {
-        T *dst = reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE);
-        const T *src = in + (size_t)(oy0 + P.shift_y) * P.w + (ox0 + P.shift_x - XOFF);
-        for (int r = tid / 32; r < C::BH; r += 8)
-          for (int c = tid % 32; c < C::BW; c += 32)
-            cp_async_elem<(int)sizeof(T)>(dst + r * C::BW + c, src + (size_t)r * P.w + c);
+        // a warp per box row, the widest copies the row's alignment allows (mb_tma.cuh)
+        stage_box<T, C::BH, C::BW, 8>(reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE), in, in, P.h, P.w, oy0 + P.shift_y,
+                                      ox0 + P.shift_x - XOFF, tid);
       }
     }
     cp_async_commit();

@@ -152,11 +152,9 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
       int oy0, ox0;
       tile_origin(i, oy0, ox0);
       if (box_inside(oy0, ox0)) {
-        T *dst = reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE);
-        const T *src = in + (size_t)(oy0 + P.shift_y) * P.in_w + (ox0 + P.shift_x - XOFF);
-        for (int r = tid / 32; r < C::BH; r += 8)
-          for (int c = tid % 32; c < C::BW; c += 32)
-            cp_async_elem<(sizeof(T) >= 4 ? (int)sizeof(T) : 4)>(dst + r * C::BW + c, src + (size_t)r * P.in_w + c);
+        // a warp per box row, the widest copies the row's alignment allows (mb_tma.cuh)
+        stage_box<T, C::BH, C::BW, 8>(reinterpret_cast<T *>(smem + (i % C::S) * C::STAGE), in, in, P.in_h, P.in_w, oy0 + P.shift_y,
+                                      ox0 + P.shift_x - XOFF, tid);
       }
     }
     cp_async_commit();

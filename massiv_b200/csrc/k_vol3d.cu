@@ -134,16 +134,9 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
     }
     if (!TMA) {  // one commit group per load, empty when the box goes through the border rule at acquire time
       if (cp_ok(zsrc, oy0, ox0)) {
-        T *dst = reinterpret_cast<T *>(smem + s * C::STAGE);
-        const int y0 = oy0 + P.sy - 1, x0 = ox0 + P.sx - V;
-        const bool z_ok = zsrc >= 0 && zsrc < P.in_d;
-        for (int e = tid; e < C::BW * C::BH; e += 256) {
-          const int r = e / C::BW, cc = e - r * C::BW;
-          const int gy = y0 + r, gx = x0 + cc;
-          const bool ok = z_ok && gy >= 0 && gy < P.in_h && gx >= 0 && gx < P.in_w;
-          const T *src = ok ? in + ((size_t)zsrc * P.in_h + gy) * P.in_w + gx : in;
-          cp_async_elem<(int)sizeof(T)>(dst + e, src, ok ? (int)sizeof(T) : 0);
-        }
+        // a warp per box row, the widest copies the row's alignment allows; zeros outside the array (mb_tma.cuh)
+        const T *pl = (zsrc >= 0 && zsrc < P.in_d) ? in + (size_t)zsrc * P.in_h * P.in_w : nullptr;
+        stage_box<T, C::BH, C::BW, 8>(reinterpret_cast<T *>(smem + s * C::STAGE), pl, in, P.in_h, P.in_w, oy0 + P.sy - 1, ox0 + P.sx - V, tid);
       }
       cp_async_commit();
     }

@@ -19,10 +19,14 @@
 #include "mb_tma.cuh"
 
 #ifndef MB_TB2_R
-#define MB_TB2_R 4  // rows per thread (tile height 8 * R)
+#define MB_TB2_R 4  // rows per thread (tile height MB_TB2_NW * R)
+#endif
+#ifndef MB_TB2_NW
+#define MB_TB2_NW 12  // warps per CTA: a warp owns R rows of the tile.  12 x 4 = 48-row tiles, one CTA of 384 threads per SM
+                      // with 160 registers each: measured best of 8 / 10 / 12 / 14 / 16 warps x 2..6 rows
 #endif
 #ifndef MB_TB2_MINB
-#define MB_TB2_MINB 2
+#define MB_TB2_MINB (MB_TB2_NW <= 8 ? 2 : 1)
 #endif
 #ifndef MB_TB2_S
 #define MB_TB2_S 4
@@ -48,12 +52,13 @@ template <typename T> struct Coef27b {
 template <typename T, int R_> struct TB2Cfg {
   static constexpr int V = 16 / (int)sizeof(T);
   static constexpr int R = R_;
-  static constexpr int TXB = 32 * V, TYB = 8 * R;      // stage-1 tile
+  static constexpr int NT = 32 * MB_TB2_NW;            // threads per CTA
+  static constexpr int TXB = 32 * V, TYB = MB_TB2_NW * R;  // stage-1 tile
   static constexpr int OX = TXB - 2 * V, OY = TYB - 2;  // result tile
   static constexpr int BW = TXB + 2 * V, BH = TYB + 2;  // staged box (one-cell halo, vector-padded in x)
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
   static constexpr int S = MB_TB2_S;
-  static constexpr int SMEM = (S + 2) * STAGE + 64;     // S source stages + 2 intermediate planes
+  static constexpr int SMEM = (S + 2) * STAGE + 128;    // S source stages + 2 intermediate planes + barriers + the producer's books
 };
 
 template <typename T> __device__ __forceinline__ void lds_v(T *dst, const T *src) {
@@ -65,33 +70,70 @@ template <typename T> __device__ __forceinline__ void lds_v(T *dst, const T *src
   for (int v = 0; v < V; ++v) dst[v] = tmp[v];
 }
 
-// one application on the thread's R x V cells: planes below / at / above in registers (pm, pc, pp),
-// the in-plane neighbours of the middle plane from shared memory (`mid` points at the thread's first
-// cell, row pitch BW).  Kernel index order 4,10,12,13,14,16,22; see k_vol3d.cu.
-template <typename T, bool REV, int R, int V, int BW, bool SIGNAL = false>
-__device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T (&pc)[R][V], const T (&pp)[R][V],
-                                      const Coef27b<T> &K, T (&res)[R][V], uint64_t *done = nullptr) {
-  using A = Arith<T>;
+// The in-plane neighbours one application needs beyond the thread's own R x V cells of the middle plane: the row
+// above / below (a vector each) and the cell left / right of every row.
+template <typename T, int R, int V> struct Nbrs {
   T ytop[V], ybot[V], xl[R], xr[R];
-  lds_v<T>(ytop, mid - BW);
-  lds_v<T>(ybot, mid + R * BW);
+};
+
+// experiment switches (each measured on the GPU before it became a default)
+#ifndef MB_TB2_BOOKS_SMEM
+#define MB_TB2_BOOKS_SMEM 0  // 1: the TMA producer's bookkeeping lives in shared memory instead of registers
+#endif
+#ifndef MB_TB2_INSIDE
+#define MB_TB2_INSIDE 1      // 1: tiles that lie inside the array skip the masking of the intermediate values (uniform branch)
+#endif
+#ifndef MB_TB2_TRACKALL
+#define MB_TB2_TRACKALL 1    // 1: the finite check inspects every result (rim included), stores are predicated, no per-row branches
+#endif
+#ifndef MB_TB2_HOIST
+#define MB_TB2_HOIST 0  // 1: the in-plane neighbour loads of stage 1 are issued before the wait for the new source plane
+#endif
+#ifndef MB_TB2_SHFL
+#define MB_TB2_SHFL 0  // 1: x neighbours come from the adjacent lanes' registers (warp shuffle) instead of shared memory
+#endif
+
+// `mid` points at the thread's first cell of the middle plane in shared memory (row pitch BW); pc are the same
+// cells in registers.  Lane stride is one 16-byte vector, so the scalar xl / xr loads are two-way bank
+// conflicted; with MB_TB2_SHFL they travel by shuffle and only lanes 0 / 31 touch shared memory.
+template <typename T, int R, int V, int BW>
+__device__ __forceinline__ void load_nbrs(const T *mid, const T (&pc)[R][V], Nbrs<T, R, V> &nb) {
+  lds_v<T>(nb.ytop, mid - BW);
+  lds_v<T>(nb.ybot, mid + R * BW);
+#if MB_TB2_SHFL
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    xl[r] = mid[r * BW - 1];
-    xr[r] = mid[r * BW + V];
+    T l = __shfl_up_sync(0xffffffffu, pc[r][V - 1], 1);
+    T rr = __shfl_down_sync(0xffffffffu, pc[r][0], 1);
+    if (lane == 0) l = mid[r * BW - 1];
+    if (lane == 31) rr = mid[r * BW + V];
+    nb.xl[r] = l;
+    nb.xr[r] = rr;
   }
-  if (SIGNAL) {  // this warp's reads of the plane are done: one arrival per warp
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(done);
+#else
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    nb.xl[r] = mid[r * BW - 1];
+    nb.xr[r] = mid[r * BW + V];
   }
+#endif
+}
+
+// one application on the thread's R x V cells: planes below / at / above in registers (pm, pc, pp).
+// Kernel index order 4,10,12,13,14,16,22; see k_vol3d.cu.
+template <typename T, bool REV, int R, int V>
+__device__ __forceinline__ void star7(const Nbrs<T, R, V> &nb, const T (&pm)[R][V], const T (&pc)[R][V], const T (&pp)[R][V],
+                                      const Coef27b<T> &K, T (&res)[R][V]) {
+  using A = Arith<T>;
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const T up = r > 0 ? pc[r - 1][v] : ytop[v];
-      const T dn = r + 1 < R ? pc[r + 1][v] : ybot[v];
-      const T lf = v > 0 ? pc[r][v - 1] : xl[r];
-      const T rt = v + 1 < V ? pc[r][v + 1] : xr[r];
+      const T up = r > 0 ? pc[r - 1][v] : nb.ytop[v];
+      const T dn = r + 1 < R ? pc[r + 1][v] : nb.ybot[v];
+      const T lf = v > 0 ? pc[r][v - 1] : nb.xl[r];
+      const T rt = v + 1 < V ? pc[r][v + 1] : nb.xr[r];
       T acc = A::from_count(0);
       acc = A::add(A::mul(REV ? pp[r][v] : pm[r][v], K.k[4]), acc);
       acc = A::add(A::mul(REV ? dn : up, K.k[10]), acc);
@@ -104,6 +146,36 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
     }
 }
 
+// Inf / NaN detection on the integer pipe without masking the sign: a positive non-finite value has the largest
+// high word among the positives (signed maximum), a negative one the largest among all as unsigned.
+#ifndef MB_TB2_TRACK2
+#define MB_TB2_TRACK2 1
+#endif
+struct Finite2 {
+  int smax = 0;
+  unsigned umax = 0;
+};
+template <typename T, int N> __device__ __forceinline__ void track_row(Finite2 &f, const T (&x)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi;
+    if constexpr (sizeof(T) == 8) hi = __double2hiint(x[i]); else hi = __float_as_int(x[i]);
+#if MB_TB2_TRACK2
+    f.smax = max(f.smax, hi);
+    f.umax = max(f.umax, (unsigned)hi);
+#else
+    f.umax = max(f.umax, (unsigned)hi & 0x7fffffffu);
+#endif
+  }
+}
+template <typename T> __device__ __forceinline__ bool nonfinite_seen(const Finite2 &f) {
+#if MB_TB2_TRACK2
+  return sizeof(T) == 8 ? (f.smax >= 0x7ff00000 || f.umax >= 0xfff00000u) : (f.smax >= 0x7f800000 || f.umax >= 0xff800000u);
+#else
+  return f.umax >= (sizeof(T) == 8 ? 0x7ff00000u : 0x7f800000u);
+#endif
+}
+
 // DETECT: no finite-input promise.  The kernel reports through `flag` whether an Inf or NaN was involved
 // — in the source or in the intermediate array (a finite input can overflow); the caller then redoes the
 // two steps with the strict 27-tap kernel (conditional launches that return at once when the flag is
@@ -111,25 +183,31 @@ __device__ __forceinline__ void star7(const T *mid, const T (&pm)[R][V], const T
 // inspects the RESULTS only: a non-finite value at a cell makes the next application's value at the same
 // cell non-finite through the centre tap, so it always surfaces in the result tile that owns the cell.
 template <typename T, bool REV, int R_, int DETECT, bool TMA>
-__global__ void __launch_bounds__(256, MB_TB2_MINB)
+__global__ void __launch_bounds__(32 * MB_TB2_NW, MB_TB2_MINB)
 vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, const Coef27b<T> K, const T *__restrict__ in,
                  T *__restrict__ out, unsigned *flag) {
-  unsigned bad = 0;
+  Finite2 bad;
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
+  constexpr int SP = C::BW;         // row pitch of a staged source plane
+  constexpr int SSTAGE = C::STAGE;  // bytes per source stage
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char *const ubase = smem + S * C::STAGE;  // two intermediate planes, STAGE bytes apart
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (S + 2) * C::STAGE);
+  unsigned char *const ubase = smem + S * SSTAGE;  // two intermediate planes (row pitch BW), STAGE bytes apart
+  uint64_t *full = reinterpret_cast<uint64_t *>(ubase + 2 * C::STAGE);
   uint64_t *ufree = full + S;  // "every warp has read intermediate buffer b": it may be overwritten
   const int tid = threadIdx.x;
   if (tid == 0) {
     if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-    mbar_init(&ufree[0], 8);
-    mbar_init(&ufree[1], 8);
+    mbar_init(&ufree[0], MB_TB2_NW);
+    mbar_init(&ufree[1], MB_TB2_NW);
     fence_mbar_init();
   }
+  // The rim of the two intermediate buffers (box cells outside the stage-1 tile) is never written by a step;
+  // the result cells that read it are themselves rim cells and never stored, but they ARE inspected by the
+  // finite check, so the rim holds zeros rather than whatever the last kernel left in shared memory.
+  for (int e = tid; e < 2 * C::STAGE / (int)sizeof(T); e += C::NT) reinterpret_cast<T *>(ubase)[e] = T(0);
   __syncthreads();
 
   const int my_items = (P.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -145,68 +223,70 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   // producer (thread 0): source planes numbered over this CTA's items; an item of nz result planes
   // consumes nz + 4 source planes (two above, two below).  The next load's coordinates are kept
   // incrementally so that the steady state costs a handful of instructions.
-  int p_it = 0, p_left = 0, p_x = 0, p_y = 0, p_z = 0, issued = 0, total_loads = 0;
-  if (tid == 0 || !TMA) {  // (without TMA every thread keeps the producer's books: all of them copy)
+  // With TMA only thread 0 produces: its books live in shared memory so that they do not occupy registers in
+  // every thread of a kernel that sits at the 128-register limit.  (Without TMA every thread copies and keeps
+  // them in registers.)
+  struct Books { int it, left, x, y, z, issued, total; };
+  Books *const pb = reinterpret_cast<Books *>(ufree + 2);
+  constexpr bool BOOKS_SMEM = TMA && MB_TB2_BOOKS_SMEM;
+  Books rb = {0, 0, 0, 0, 0, 0, 0};
+  if (tid == 0 || !TMA) {
     for (int it = 0; it < my_items; ++it) {
       int a, nz, b, c;
       item_geom(it, a, nz, b, c);
-      total_loads += nz + 4;
+      rb.total += nz + 4;
     }
+    if (BOOKS_SMEM) *pb = rb;
   }
   auto issue_upto = [&](int limit) {  // limit = planes released so far + S
-    while (issued < total_loads && issued < limit) {
-      if (p_left == 0) {
+    Books q = BOOKS_SMEM ? *pb : rb;
+    while (q.issued < q.total && q.issued < limit) {
+      if (q.left == 0) {
         int oz0, nz, oy0, ox0;
-        item_geom(p_it++, oz0, nz, oy0, ox0);
-        p_left = nz + 4;
-        p_x = ox0 - 2 * V; p_y = oy0 - 2; p_z = oz0 + P.sz2 - 2;
+        item_geom(q.it++, oz0, nz, oy0, ox0);
+        q.left = nz + 4;
+        q.x = ox0 - 2 * V; q.y = oy0 - 2; q.z = oz0 + P.sz2 - 2;
       }
-      const int s = issued % S;
+      const int s = q.issued % S;
       if (TMA) {
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
-        tma_load_3d(smem + s * C::STAGE, &tmap, &full[s], p_x, p_y, p_z);
+        tma_load_3d(smem + s * SSTAGE, &tmap, &full[s], q.x, q.y, q.z);
       } else {
-        // the whole CTA copies the box; cells outside the array are written as zeros (src-size 0), which
-        // is what TMA's out-of-range fill does.  One commit group per plane.
-        T *dst = reinterpret_cast<T *>(smem + s * C::STAGE);
-        const bool z_ok = p_z >= 0 && p_z < P.in_d;
-        for (int e = tid; e < C::BW * C::BH; e += 256) {
-          const int r = e / C::BW, cc = e - r * C::BW;
-          const int gy = p_y + r, gx = p_x + cc;
-          const bool ok = z_ok && gy >= 0 && gy < P.in_h && gx >= 0 && gx < P.in_w;
-          const T *src = ok ? in + ((size_t)p_z * P.in_h + gy) * P.in_w + gx : in;
-          cp_async_elem<(int)sizeof(T)>(dst + e, src, ok ? (int)sizeof(T) : 0);
-        }
+        // the whole CTA copies the box, a warp per row with the widest copies the row's alignment allows; cells
+        // outside the array become zeros, as with TMA (mb_tma.cuh).  One commit group per plane.
+        const T *pl = (q.z >= 0 && q.z < P.in_d) ? in + (size_t)q.z * P.in_h * P.in_w : nullptr;
+        stage_box<T, C::BH, C::BW, MB_TB2_NW>(reinterpret_cast<T *>(smem + s * SSTAGE), pl, in, P.in_h, P.in_w, q.y, q.x, tid);
         cp_async_commit();
       }
-      ++issued; ++p_z; --p_left;
+      ++q.issued; ++q.z; --q.left;
     }
+    if (BOOKS_SMEM) *pb = q; else rb = q;
   };
   if (tid == 0 || !TMA) issue_upto(S);
 
-  uint32_t phase = 0;
   auto acquire = [&](int L) {
     const int s = L % S;
     if (TMA) {
-      mbar_wait(&full[s], (phase >> s) & 1u);
-      phase ^= 1u << s;
+      mbar_wait(&full[s], (uint32_t)(L / S) & 1u);  // load L is the (L / S)-th use of its stage
     } else {
       // plane L's group must have landed; issued - 1 - L younger groups may still be in flight
-      switch (issued - 1 - L) {
-        case 0: cp_async_wait_group<0>(); break;
-        case 1: cp_async_wait_group<1>(); break;
-        case 2: cp_async_wait_group<2>(); break;
-        default: cp_async_wait_group<3>(); break;
-      }
+      const int younger = rb.issued - 1 - L;
+      if (younger <= 0) cp_async_wait_group<0>();
+      else if (younger == 1) cp_async_wait_group<1>();
+      else if (younger == 2) cp_async_wait_group<2>();
+      else if (younger == 3) cp_async_wait_group<3>();
+      else if (younger == 4) cp_async_wait_group<4>();
+      else cp_async_wait_group<5>();
       __syncthreads();  // everybody's share of the plane is visible
     }
   };
   const int lx = (tid % 32) * V, ly = (tid / 32) * R;
-  const int coff = (ly + 1) * BW + V + lx;  // the thread's first cell inside a staged box
+  const int coff = (ly + 1) * BW + V + lx;   // the thread's first cell inside an intermediate plane
+  const int scoff = (ly + 1) * SP + V + lx;  // ... inside a staged source box
   auto centres = [&](T (&dst)[R][V], int L) {
-    const T *sp = reinterpret_cast<const T *>(smem + (L % S) * C::STAGE) + coff;
+    const T *sp = reinterpret_cast<const T *>(smem + (L % S) * SSTAGE) + scoff;
 #pragma unroll
-    for (int r = 0; r < R; ++r) lds_v<T>(dst[r], sp + r * BW);
+    for (int r = 0; r < R; ++r) lds_v<T>(dst[r], sp + r * SP);
   };
 
   int Lc = 0;
@@ -225,9 +305,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     centres(Z1, Lc + 1);
     if (DETECT) {  // the two planes below the item's first result plane are nobody's result in this launch
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int v = 0; v < V; ++v) { track_magnitude(bad, Z0[r][v]); track_magnitude(bad, Z1[r][v]); }
+      for (int r = 0; r < R; ++r) { track_row(bad, Z0[r]); track_row(bad, Z1[r]); }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -235,17 +313,16 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       for (int v = 0; v < V; ++v) U0[r][v] = U1[r][v] = T(0);
     // which of the thread's cells exist in the global array (the intermediate is Fill 0 elsewhere),
     // and which of its rows are result cells (the tile minus its rim, inside the array)
-    uint32_t in_yx = 0, rows = 0;
-    const int gx = xB0 + lx;
+    uint32_t rows = 0;
+    const int gx = xB0 + lx, gy0 = yB0 + ly;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int by = ly + r, gy = yB0 + by;
-      if (gy >= 0 && gy < P.in_h) in_yx |= 1u << r;
       if (by >= 1 && by < C::TYB - 1 && lx >= V && lx < C::TXB - V && gy < P.in_h && gx < P.in_w) rows |= 1u << r;
     }
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (gx + v >= 0 && gx + v < P.in_w) in_yx |= 0x100u << v;
+    // CTA-uniform: the whole stage-1 tile lies inside the array in y and x (true for all but the edge tiles):
+    // the intermediate values then need no masking on planes inside the array
+    const bool tile_inside = yB0 >= 0 && yB0 + C::TYB <= P.in_h && xB0 >= 0 && xB0 + C::TXB <= P.in_w;
     const bool whole = P.vec_store && gx + V <= P.in_w;
     const long long plane = (long long)P.in_h * P.in_w;
     long long ooff = ((long long)oz0 * P.in_h + (yB0 + ly)) * P.in_w + gx;  // row 0 of result plane oz0 (used where rows says so)
@@ -254,29 +331,40 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     auto step = [&](int k, const T (&zm)[R][V], const T (&zc)[R][V], T (&zp)[R][V], const T (&um)[R][V], const T (&uc)[R][V],
                     T (&up)[R][V]) {
       const int ip = cs - 1 + k;  // intermediate plane produced in this step (source frame)
+      // the middle source plane has been resident since the last step: its in-plane neighbours are fetched
+      // before the wait for the new plane, so their latency overlaps it
+      Nbrs<T, R, V> nb;
+#if MB_TB2_HOIST
+      load_nbrs<T, R, V, SP>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * SSTAGE) + scoff, zc, nb);
+#endif
       acquire(Lc + k + 2);
       centres(zp, Lc + k + 2);
+#if !MB_TB2_HOIST
+      load_nbrs<T, R, V, SP>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * SSTAGE) + scoff, zc, nb);
+#endif
       if (DETECT == 2 || (DETECT == 1 && k >= nz)) {  // ... nor are the two planes above its last one
+#pragma unroll
+        for (int r = 0; r < R; ++r) track_row(bad, zp[r]);
+      }
+      // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
+      star7<T, REV, R, V>(nb, zm, zc, zp, K, up);
+      const bool in_z = ip + P.zoff >= 0 && ip + P.zoff < P.dglob;
+      T *ub = reinterpret_cast<T *>(ubase + (g & 1u) * C::STAGE) + coff;
+      if (!MB_TB2_INSIDE || !(tile_inside && in_z)) {  // uniform: edge tiles and the planes beyond the array's ends only
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int v = 0; v < V; ++v) track_magnitude(bad, zp[r][v]);
+          for (int v = 0; v < V; ++v)
+            if (!(in_z && (unsigned)(gy0 + r) < (unsigned)P.in_h && (unsigned)(gx + v) < (unsigned)P.in_w)) up[r][v] = T(0);
       }
-      // ---- stage 1: first application, planes ip-1, ip, ip+1 of the source ----
-      star7<T, REV, R, V, BW>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * C::STAGE) + coff, zm, zc, zp, K, up);
-      const bool in_z = ip + P.zoff >= 0 && ip + P.zoff < P.dglob;
-      T *ub = reinterpret_cast<T *>(ubase + (g & 1u) * C::STAGE) + coff;
+      if (DETECT == 2 || (DETECT == 1 && (k == 0 || k == nz + 1))) {  // intermediate planes outside the result range
+#pragma unroll
+        for (int r = 0; r < R; ++r) track_row(bad, up[r]);
+      }
       // the buffer was last read by step g-1's second application
       if (g > 0) mbar_wait(&ufree[g & 1u], ((g - 1) >> 1) & 1u);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (!(in_z && ((in_yx >> r) & 1u) && ((in_yx >> (8 + v)) & 1u))) up[r][v] = T(0);
-        if (DETECT == 2 || (DETECT == 1 && (k == 0 || k == nz + 1))) {  // intermediate planes outside the result range
-#pragma unroll
-          for (int v = 0; v < V; ++v) track_magnitude(bad, up[r][v]);
-        }
         uint4 q;
         memcpy(&q, up[r], 16);
         *reinterpret_cast<uint4 *>(ub + r * BW) = q;
@@ -286,16 +374,39 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       // ---- stage 2: second application one plane behind, intermediate planes ip-2, ip-1, ip ----
       const T *umid = reinterpret_cast<const T *>(ubase + ((g + 1u) & 1u) * C::STAGE) + coff;
       if (k >= 2) {
+        load_nbrs<T, R, V, BW>(umid, uc, nb);
+        __syncwarp();  // this warp's reads of the plane are done: one arrival per warp
+        if ((tid & 31) == 0) mbar_arrive(&ufree[(g + 1u) & 1u]);
         T res[R][V];
-        star7<T, REV, R, V, BW, true>(umid, um, uc, up, K, res, &ufree[(g + 1u) & 1u]);
+        star7<T, REV, R, V>(nb, um, uc, up, K, res);
+#if MB_TB2_TRACKALL
+        if (DETECT == 1) {
+          // every cell's result is inspected, rim cells included (they are computed from finite-or-real data:
+          // the buffers' rim was zeroed), so the check is branch-free
+#pragma unroll
+          for (int r = 0; r < R; ++r) track_row(bad, res[r]);
+        }
+        T *dst = out + ooff;
+        if (whole) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            uint4 q;
+            memcpy(&q, res[r], 16);
+            if ((rows >> r) & 1u) *reinterpret_cast<uint4 *>(dst + (size_t)r * P.in_w) = q;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              if (((rows >> r) & 1u) && gx + v < P.in_w) dst[(size_t)r * P.in_w + v] = res[r][v];
+        }
+#else
         T *dst = out + ooff;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if ((rows >> r) & 1u) {
-            if (DETECT == 1) {
-#pragma unroll
-              for (int v = 0; v < V; ++v) track_magnitude(bad, res[r][v]);
-            }
+            if (DETECT == 1) track_row(bad, res[r]);
             if (whole) {
               uint4 q;
               memcpy(&q, res[r], 16);
@@ -307,6 +418,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
             }
           }
         }
+#endif
         ooff += plane;
       } else {
         __syncwarp();
@@ -326,7 +438,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     }
     Lc += nz + 4;
   }
-  if (DETECT && magnitude_nonfinite<T>(bad)) atomicOr(flag, 1u);
+  if (DETECT && nonfinite_seen<T>(bad)) atomicOr(flag, 1u);
 }
 
 template <typename T, bool REV, int R_, int DETECT>
@@ -353,11 +465,12 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   auto kern_tma = vol3d_tb2_kernel<T, REV, R_, DETECT, true>;
   auto kern_cp = vol3d_tb2_kernel<T, REV, R_, DETECT, false>;
   auto kern = P.use_tma ? kern_tma : kern_cp;
+  const int smem_bytes = C::SMEM;
   static int occ_dev[64][2] = {{0}};
   int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {
-    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem_bytes));
     if (occ < 1) occ = 1;
   }
   const int resident = c->num_sms * occ;
@@ -380,7 +493,7 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   }
   P.nitems = tiles * chunks;
   const int grid = resident < P.nitems ? resident : P.nitems;
-  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out, flag);
+  kern<<<grid, C::NT, smem_bytes, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out, flag);
   c->launches++;
   c->last_kernel = "vol3d_tb2";
   return check_cuda(c, cudaGetLastError(), "vol3d_tb2_kernel launch");
@@ -463,6 +576,10 @@ int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const
                      int64_t dglob, unsigned *detect) {
   const bool rev = p.kind == MB_CONV;
 #define MB_TB2_GO(T, REV, DET) launch_tb2_r<T, REV, MB_TB2_R, DET>(c, p, d_in, d_out, range, sz2, zoff, dglob, detect)
+#ifdef MB_TB2_QUICK  // compile-time experiments: only the Double convolution instantiations
+  if (p.elem != MB_F64 || !rev) return -1;
+  return detect ? MB_TB2_GO(double, true, 1) : MB_TB2_GO(double, true, 0);
+#else
   if (p.elem == MB_F64) {
     const bool centre = reinterpret_cast<const double *>(p.c1.data())[13] != 0.0;
     if (detect && centre) return rev ? MB_TB2_GO(double, true, 1) : MB_TB2_GO(double, false, 1);
@@ -473,6 +590,7 @@ int launch_vol3d_tb2(Ctx *c, const Plan &p, const void *d_in, void *d_out, const
   if (detect && centre) return rev ? MB_TB2_GO(float, true, 1) : MB_TB2_GO(float, false, 1);
   if (detect) return rev ? MB_TB2_GO(float, true, 2) : MB_TB2_GO(float, false, 2);
   return rev ? MB_TB2_GO(float, true, 0) : MB_TB2_GO(float, false, 0);
+#endif
 #undef MB_TB2_GO
 }
 

@@ -57,6 +57,8 @@ int get_dev_plan(Ctx *c, const mb_stencil_desc *d, const int64_t *in_dims, std::
   key.append((const char *)p.c1.data(), p.c1.size());
   key.append((const char *)p.c2.data(), p.c2.size());
   key.append((const char *)p.post.data(), p.post.size() * sizeof(mb_post_op));
+  key.append((const char *)p.terms.data(), p.terms.size() * sizeof(Plan::Term));
+  key.append((const char *)p.prog.data(), p.prog.size() * sizeof(mb_xins));
   auto it = c->plans.find(key);
   if (it != c->plans.end()) { *out = it->second; return MB_OK; }
   if (c->plans.size() > 256) c->plans.clear();  // bounded; shared_ptrs keep in-flight plans alive

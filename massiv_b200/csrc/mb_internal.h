@@ -39,6 +39,16 @@ struct Plan {
   std::vector<uint8_t> c1, c2;           // ntaps coefficients each (elem bytes), may be empty
   uint8_t fill[8] = {0};
   std::vector<mb_post_op> post;          // fmap'ed functions applied to every result, in order
+  // MB_EXPR: the sub-stencils ("terms") whose values the postfix program combines.  Their taps and coefficients
+  // are concatenated in tap_off / c1 (term t owns [begin, begin + ntaps)); ntaps is the total.
+  struct Term {
+    int32_t kind;      // mb_kind of the term
+    int32_t begin;     // first tap in tap_off / c1
+    int32_t ntaps;
+    int32_t avg_n;     // AVG: totalElem of the term's size
+  };
+  std::vector<Term> terms;
+  std::vector<mb_xins> prog;
   int64_t in_elems = 0, out_elems = 0;
   bool dense = false;                    // taps form the full [0,size) window (fold/conv/corr/mag2)
   bool descending = false;               // dense taps visited with descending offsets (conv)
