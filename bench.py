@@ -23,6 +23,8 @@ Workloads (BASELINE.json configs):
     gauss7sep  same, separable two-pass (mb_run_sep2)
     life     Game of Life Word8, Wrap, 2048^2, iterated
     pool3 / simpson   SURVEY §8 (f) rows: strided evaluation
+    sobel_operator / sobel_closure   the reference's published Sobel benchmark (closure-form stencils) at its own size and large
+    sum9x9_u8   a 9x9 window over a Word8 image (small-window kernel)
 
 `--impl reference` times the CPU restatement of massiv's Par path (oracle/, a pinned number of host threads) on a
 bounded sample of the same workload: no GHC exists in this image, so massiv itself cannot run.
@@ -58,6 +60,17 @@ WORKLOADS = {
     # strided evaluation.  Cells are OUTPUT cells; bytes are input + output.
     "pool3": dict(dtype="i64", grid=(24576, 24576), stride=(3, 3), iterated=False, config_id="f1",
                   text="computeWithStride (Stride 3) . mapStencil Edge (maxStencil (Sz 3)), Int (Stencil.hs:360-364 at scale)"),
+    # the reference's OWN published benchmark (massiv/README.md:598-632, "Sobel/Par/Operator - Massiv"): the closure-form
+    # Sobel operator of massiv-bench/src/Data/Massiv/Bench/Sobel.hs:15-44, 1600x1200 Double, Edge — 7.421 ms on a
+    # 4-core i7-3740QM.  sobel_operator is that exact size (L2-resident: a latency figure), sobel_closure the same
+    # operator on an array larger than L2.  Both run the small-window kernel (two tap lists + sqrt (x*x + y*y)).
+    "sobel_operator": dict(dtype="f64", grid=(1600, 1200), bpc=16, iterated=False, config_id="published",
+                           published_gcells=1600 * 1200 / 7.421e-3 / 1e9,
+                           text="Sobel operator, closure form (makeConvolutionStencil), Double 1600x1200, Edge: the reference's published benchmark"),
+    "sobel_closure": dict(dtype="f64", grid=(16384, 16384), bpc=16, iterated=False, config_id="a13",
+                          text="Sobel operator, closure form (makeConvolutionStencil x2, sqrt (sX*sX + sY*sY)), Double 16384^2, Edge"),
+    "sum9x9_u8": dict(dtype="u8", grid=(32768, 32768), bpc=2, iterated=False, config_id="a17", u8_full=True,
+                      text="sumStencil (Sz2 9 9) Word8 (mod 256), Edge, 32768^2: a 9x9 window on a byte image"),
     "simpson": dict(dtype="f64", grid=(16384, 16385), stride=(1, 16), iterated=False, config_id="f2",
                     text="integrateWith simpsonsStencil (Dim 1) 16: Simpson's rule along the rows, Double, Fill 0 "
                          "(Numeric/Integral.hs:99-135)"),
@@ -67,7 +80,9 @@ SIMPSON_DX = 1.0 / 16.0
 # the other BASELINE configs, measured after the headline in the default N=1 run: (workload, timed steps)
 # (Life: 1000 generations per call as the config says; the single passes repeat until the timed region is long
 # enough for the clock sampler to see it)
-CONFIG_RUNS = [("life", 1000), ("avg3x3", 200), ("sobel", 100), ("gauss7", 50), ("gauss7sep", 100)]
+CONFIG_RUNS = [("life", 1000), ("avg3x3", 200), ("sobel", 100), ("gauss7", 50), ("gauss7sep", 100),
+               # beyond BASELINE.json's list: the reference's published benchmark and the small-window kernel's proofs
+               ("sobel_operator", 2000), ("sobel_closure", 50), ("sum9x9_u8", 20)]
 # measured unfused FP32 rate (mul and add issued separately, scripts/micro/fp_rate.cu on this pool's B200)
 FP32_OPS_PER_S = 35.0e12
 REF_THREADS = 16  # the reference arm and cpu_baseline use min(this, host cores) threads so that ratios compare across boxes
@@ -126,8 +141,25 @@ def oracle_spec(name):
     raise KeyError(name)
 
 
+def oracle_from_desc(O, dw, a, threads, stride=None):
+    """the CPU oracle on the very descriptor the product would run (the two structures share their layout)"""
+    d = dw.desc(stride)
+    od = O._Desc.from_buffer_copy(bytes(d))
+    dims = O._dims(a.shape)
+    out_dims = (C.c_int64 * O.MAX_RANK)()
+    assert O.lib().mo_out_dims(C.byref(od), dims, out_dims) == 0
+    out = np.empty(tuple(out_dims[i] for i in range(a.ndim)), a.dtype)
+    st = O.lib().mo_apply(C.byref(od), dims, np.ascontiguousarray(a).ctypes.data, out.ctypes.data, threads)
+    assert st == 0, st
+    return out
+
+
 def oracle_pass(O, name, a, threads):
     """one pass of the workload through the CPU oracle (gauss7sep: massiv's two computes, intermediate rounded)"""
+    if name in ("sobel_operator", "sobel_closure", "sum9x9_u8"):
+        import massiv_b200 as M   # host-side lowering only (numpy in, descriptor out): no device involved
+        spec = stencil_spec(name, M)
+        return oracle_from_desc(O, M.mapStencil(spec[0], spec[1], a), a, threads)
     if name == "gauss7sep":
         g = gauss7().tolist()
         t = O.apply("conv", a, size=(1, 7), coeffs=g, border="edge", nthreads=threads)
@@ -158,6 +190,13 @@ def stencil_spec(name, M):
         return M.Wrap, M.lifeStencil
     if name == "pool3":
         return M.Edge, M.maxStencil(M.Sz(3, 3))
+    if name in ("sobel_operator", "sobel_closure"):
+        # Bench/Sobel.hs:15-37: makeConvolutionStencil (Sz 3) (1 :. 1) $ \f -> f (-1 :. -1) (-1) . f (0 :. -1) (-2) . ...
+        sx = M.makeConvolutionStencil(M.Sz(3, 3), (1, 1), [((-1, -1), -1), ((0, -1), -2), ((1, -1), -1), ((-1, 1), 1), ((0, 1), 2), ((1, 1), 1)])
+        sy = M.makeConvolutionStencil(M.Sz(3, 3), (1, 1), [((-1, -1), -1), ((-1, 0), -2), ((-1, 1), -1), ((1, -1), 1), ((1, 0), 2), ((1, 1), 1)])
+        return M.Edge, M.sqrt(sx * sx + sy * sy)   # Bench/Sobel.hs:39-44
+    if name == "sum9x9_u8":
+        return M.Edge, M.sumStencil(M.Sz(9, 9))
     if name == "simpson":
         from massiv_b200 import integral as I
         return M.Fill(0.0), I.simpsonsStencil(np.float64(SIMPSON_DX), 1, 16)
@@ -184,7 +223,7 @@ def synth_host(name, shape, seed=2020, first=0):
         return ((h >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).reshape(shape)
     if dt == "i64":
         return (h >> np.uint64(11)).astype(np.int64).reshape(shape)
-    return (h >> np.uint64(63)).astype(np.uint8).reshape(shape)
+    return (h >> np.uint64(56 if WORKLOADS[name].get("u8_full") else 63)).astype(np.uint8).reshape(shape)
 
 
 def synth_device(torch, name, shape, device, seed=2020, first=0):
@@ -215,7 +254,7 @@ def synth_device(torch, name, shape, device, seed=2020, first=0):
         elif dt == "i64":
             out[a:b] = lsr(h, 11)
         else:
-            out[a:b] = lsr(h, 63).to(torch.uint8)
+            out[a:b] = lsr(h, 56 if WORKLOADS[name].get("u8_full") else 63).to(torch.uint8)
         del x, z, h
     return out.view(*shape)
 
@@ -306,7 +345,7 @@ def cpu_sample_shape(name):
         return (48, g[1], g[2]), 2
     if name == "life":
         return g, 20
-    return (4096, g[1]), 1
+    return (min(4096, g[0]), g[1]), 1
 
 
 def run_cpu(name, steps, warmup, threads=None):
@@ -315,11 +354,11 @@ def run_cpu(name, steps, warmup, threads=None):
     wl = "gauss7" if name == "gauss7sep" else name
     shape, inner = cpu_sample_shape(wl)
     a = synth_host(wl, shape)
-    kind, kw = oracle_spec(wl)
     iterated = WORKLOADS[wl]["iterated"]
 
     def once():
         if iterated:
+            kind, kw = oracle_spec(wl)
             return O.iterate(kind, a, inner, nthreads=threads, **kw)
         return oracle_pass(O, name, a, threads)
 
@@ -524,6 +563,9 @@ def measure_device(env, name, grid, steps, warmup, sharded=False, keep=None):
         # the kernel's real DRAM rate: measured traffic of one launch over the launch time measured here
         rec["roofline"]["dram_gbs"] = traffic / (per_launch_ms * 1e-3) / 1e9
         rec["roofline"]["dram_frac"] = rec["roofline"]["dram_gbs"] / peak
+    if "published_gcells" in wl:
+        rec["vs_baseline"] = value / wl["published_gcells"]
+        rec["baseline"] = {"value": wl["published_gcells"], "unit": "Gcells/s", "source": "massiv/README.md:598-632 (7.421 ms, i7-3740QM, 8 threads, GHC 8.8.4)"}
     if name == "gauss7":
         # 49 multiplies + 49 adds per cell, never fused (bit-identical to the reference): the FP32 issue rate is the
         # nearer roof for the direct form

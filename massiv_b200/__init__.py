@@ -10,7 +10,7 @@ from .stencil import (  # noqa: F401
     getStencilCenter, getStencilSize, handleBorderIndex, idStencil, iterateStencil, lifeStencil,
     makeConvolutionStencil, makeConvolutionStencilFromKernel, makeCorrelationStencil,
     makeCorrelationStencilFromKernel, makeUnsafeConvolutionStencil, makeUnsafeCorrelationStencil,
-    mapStencil, maxStencil, minStencil, noPadding, productStencil, samePadding, sqrt, sumStencil,
+    mapStencil, maxStencil, maxStencils, minStencil, minStencils, noPadding, productStencil, samePadding, sqrt, sumStencil,
 )
 
 from . import integral  # noqa: F401,E402  (Data.Massiv.Array.Numeric.Integral)

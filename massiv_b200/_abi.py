@@ -20,7 +20,7 @@ NCCL_ID_BYTES = 128
 ELEMS = {"u8": 0, "i8": 1, "u16": 2, "i16": 3, "u32": 4, "i32": 5, "u64": 6, "i64": 7, "f32": 8,
          "f64": 9, "bool32": 10}
 KINDS = {"id": 0, "sum": 1, "product": 2, "avg": 3, "max": 4, "min": 5, "conv": 6, "corr": 7,
-         "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13}
+         "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13, "expr": 14}
 BORDERS = {"fill": 0, "wrap": 1, "edge": 2, "reflect": 3, "continue": 4}
 FLAG_MAG2_CORR = 1
 FLAG_ASSUME_FINITE = 2
@@ -59,6 +59,25 @@ def post_array(post, npdt):
     return arr
 
 
+# program steps of an expression stencil (mb_xop)
+XOPS = {"term": 1, "const": 2, "add": 3, "sub": 4, "mul": 5, "div": 6, "min": 7, "max": 8, "negate": 9, "abs": 10,
+        "signum": 11, "square": 12, "recip": 13, "sqrt": 14}
+XOPS_BINARY = ("add", "sub", "mul", "div", "min", "max")
+XOPS_UNARY = ("negate", "abs", "signum", "square", "recip", "sqrt")
+MAX_TERMS, MAX_PROGRAM, MAX_STACK = 8, 32, 8
+
+
+class Term(C.Structure):
+    """mb_term: one sub-stencil of an expression"""
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("size", C.c_int64 * MAX_RANK), ("center", C.c_int64 * MAX_RANK),
+                ("coeffs", C.c_void_p), ("ntaps", C.c_int64), ("tap_offsets", C.c_void_p)]
+
+
+class XIns(C.Structure):
+    """mb_xins: one step of the postfix program"""
+    _fields_ = [("op", C.c_int32), ("arg", C.c_int32), ("operand", C.c_uint8 * 8)]
+
+
 class StencilDesc(C.Structure):
     """mb_stencil_desc"""
     _fields_ = [("kind", C.c_int32), ("elem", C.c_int32), ("rank", C.c_int32), ("border", C.c_int32),
@@ -66,7 +85,8 @@ class StencilDesc(C.Structure):
                 ("pad_lo", C.c_int64 * MAX_RANK), ("pad_hi", C.c_int64 * MAX_RANK),
                 ("stride", C.c_int64 * MAX_RANK), ("fill", C.c_uint8 * 8),
                 ("coeffs", C.c_void_p), ("coeffs2", C.c_void_p), ("ntaps", C.c_int64),
-                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p)]
+                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p),
+                ("n_terms", C.c_uint32), ("n_program", C.c_uint32), ("terms", C.c_void_p), ("program", C.c_void_p)]
 
 
 MAX_HALO = 8

@@ -1,0 +1,464 @@
+// "Any small window" rank-2 kernel: every stencil the descriptor can express over a window of up to 16 x 16 cells,
+// for every Storable element type — run-time window shape, run-time tap lists, stencil expressions (MB_EXPR: the
+// Applicative / Num / Fractional / Floating instances of Stencil, Array/Stencil/Internal.hs:83-174) and post-maps
+// evaluated in ONE pass over HBM.  It takes what the compile-time-shaped kernels (k_tile2d*.cu) decline: closure-form
+// convolutions / correlations (MB_TAPS, Stencil/Convolution.hs:44-57, 89-100 — the form the reference's own Sobel
+// benchmark uses, massiv-bench/src/Data/Massiv/Bench/Sobel.hs:15-44), windows other than 3x3 / 5x5 / 7x7 / 2x2 /
+// 1xk / kx1, Word8 / Word16 / Int16 ... images, sums / products of several stencils, fused fmap.
+//
+// Same skeleton as k_tile2d.cuh — persistent CTAs, the tile's input box staged by ONE TMA box load into an mbarrier
+// ring (cp.async copies for arrays without a tensor map, a peeled path through handleBorderIndex for edge tiles
+// under borders other than Fill 0) — but the arithmetic is table driven: every term is a list of (shared-memory
+// offset, coefficient) pairs that the CTA keeps in shared memory; a thread owns 4 x 4 outputs whose columns are 32
+// apart, so that for one tap a warp reads 32 CONSECUTIVE elements of a box row: no bank conflicts for any element
+// size, window offset or alignment.  The bound is the shared-memory pipe: one LDS per tap and output,
+// 32 lanes per clock and SM.  Tap order and the one-rounding-per-operation arithmetic are the reference's
+// (mb_arith.cuh), so results are bit-identical to the generic kernel's and to massiv's.
+#include "mb_arith.cuh"
+#include "mb_internal.h"
+#include "mb_post.cuh"
+#include "mb_tma.cuh"
+
+namespace mb {
+
+enum { SW_TW = 128, SW_TH = 32, SW_CX = 4, SW_RY = 4, SW_S = 3, SW_MAX_TAPS = 1024, SW_MAX_WIN = 16 };
+
+// internal program: the descriptor's (mb_xop) plus "post-map with a constant" steps for fused fmap
+enum { SW_X_POST = 32 };  // op = SW_X_POST + mb_post, operand = c
+
+struct SWProgram {
+  int n_terms, n_prog;
+  int term_kind[MB_MAX_TERMS], term_begin[MB_MAX_TERMS], term_ntaps[MB_MAX_TERMS], term_avg_n[MB_MAX_TERMS];
+  unsigned char op[MB_MAX_PROGRAM + MB_MAX_POST + 8], arg[MB_MAX_PROGRAM + MB_MAX_POST + 8];
+  unsigned long long operand[MB_MAX_PROGRAM + MB_MAX_POST + 8];
+};
+
+struct SWParams {
+  int in_h, in_w, out_h, out_w;
+  int shift_y, shift_x;  // source index of the window's first cell for output (0, 0)
+  int y0, y1;            // output rows produced
+  int tiles_x, ntiles;
+  int border, use_tma, zero_fill_ok;
+  int xoff;              // the window begins xoff elements into the staged row (boxes start on 16-byte boundaries)
+  int bw, bh;            // staged box, elements (bw a multiple of the vector length)
+  int stage_bytes;
+  int ntaps;             // all terms together
+  int bool_canon, skip_zero, trivial;  // trivial: one term, no program beyond it
+  unsigned long long fill_bits;
+  const int32_t *taps;   // ntaps x 2 offsets relative to the evaluated index (the plan's table)
+  const void *coef;      // ntaps coefficients (zeros where a term has none)
+  int min_dy, min_dx;
+  SWProgram X;
+};
+
+template <typename T> struct SWAcc {
+  using A = Arith<T>;
+  using Acc = typename A::Acc;
+};
+
+// one term over the thread's 16 outputs
+template <typename T>
+__device__ __forceinline__ void sw_term(int kind, int nt, int avg_n, const int *__restrict__ s_off, const T *__restrict__ s_k,
+                                        const T *__restrict__ base, int pitch, bool canon, bool skip_zero, T (&out)[SW_RY][SW_CX]) {
+  using A = Arith<T>;
+  using Acc = typename A::Acc;
+  Acc acc[SW_RY][SW_CX];
+  auto ld = [&](int off, int r, int c) -> T {
+    T v = base[off + r * pitch + 32 * c];
+    if (canon) v = (T)(v != T(0));  // Storable Bool peek: (/= 0)
+    return v;
+  };
+  switch (kind) {
+    case MB_ID:
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) out[r][c] = ld(s_off[0], r, c);
+      return;
+    case MB_SUM: case MB_AVG:
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(0);
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const int off = s_off[t];
+#pragma unroll
+        for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(acc[r][c], A::load(ld(off, r, c)));
+      }
+      if (kind == MB_AVG) {
+        const Acc n = A::from_count(avg_n);
+#pragma unroll
+        for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::div(acc[r][c], n);
+      }
+      break;
+    case MB_PRODUCT:
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(1);
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const int off = s_off[t];
+#pragma unroll
+        for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::mul(acc[r][c], A::load(ld(off, r, c)));
+      }
+      break;
+    case MB_MAX: case MB_MIN: {
+      const bool mx = kind == MB_MAX;
+      T m[SW_RY][SW_CX];
+      const T init = mx ? (canon ? T(0) : Bounds<T>::lo()) : (canon ? T(1) : Bounds<T>::hi());
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) m[r][c] = init;
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const int off = s_off[t];
+#pragma unroll
+        for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) {
+            const T x = ld(off, r, c);
+            m[r][c] = mx ? (x > m[r][c] ? x : m[r][c]) : (x < m[r][c] ? x : m[r][c]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) out[r][c] = m[r][c];
+      return;
+    }
+    default:  // MB_CONV / MB_CORR / MB_TAPS: acc = src * k + acc in the listed order (Convolution.hs:52-55, 74-78, 115-119)
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(0);
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const Acc kv = A::load(s_k[t]);
+        if (skip_zero && A::is_zero(kv)) continue;
+        const int off = s_off[t];
+#pragma unroll
+        for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(A::mul(A::load(ld(off, r, c)), kv), acc[r][c]);
+      }
+      break;
+  }
+#pragma unroll
+  for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+    for (int c = 0; c < SW_CX; ++c) out[r][c] = A::store(acc[r][c]);
+}
+
+template <typename T, bool TMA>
+__global__ void __launch_bounds__(256)
+smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SWParams P, const T *__restrict__ in, T *__restrict__ out) {
+  constexpr int V = 16 / (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + SW_S * P.stage_bytes);
+  int *s_off = reinterpret_cast<int *>(full + 8);
+  T *s_k = reinterpret_cast<T *>(s_off + ((P.ntaps + 3) & ~3));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    if (TMA) tma_prefetch_desc(&tmap);
+    for (int s = 0; s < SW_S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  const int pitch = P.bw;
+  // the tap table: shared-memory offset of every tap relative to a cell's window origin, and its coefficient
+  for (int t = tid; t < P.ntaps; t += 256) {
+    s_off[t] = (P.taps[2 * t] - P.min_dy) * pitch + (P.taps[2 * t + 1] - P.min_dx) + P.xoff;
+    s_k[t] = P.coef ? reinterpret_cast<const T *>(P.coef)[t] : T(0);
+  }
+  __syncthreads();
+
+  const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_origin = [&](int i, int &oy0, int &ox0) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    oy0 = P.y0 + (t / P.tiles_x) * SW_TH;
+    ox0 = (t % P.tiles_x) * SW_TW;
+  };
+  // may tile i be fetched by TMA?  yes when out-of-range cells are never used or zero is the border
+  auto inside = [&](int oy0, int ox0) -> bool {
+    const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
+    return by0 >= 0 && bx0 >= 0 && by0 + P.bh <= P.in_h && bx0 + P.bw <= P.in_w;
+  };
+  auto async_ok = [&](int oy0, int ox0) -> bool { return TMA && (P.zero_fill_ok || inside(oy0, ox0)); };
+  auto prefetch = [&](int i) {
+    if (!TMA || tid != 0 || i >= my_tiles) return;
+    int oy0, ox0;
+    tile_origin(i, oy0, ox0);
+    if (!async_ok(oy0, ox0)) return;
+    const int s = i % SW_S;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(P.bw * P.bh * (int)sizeof(T)));
+    tma_load_2d(smem + s * P.stage_bytes, &tmap, &full[s], ox0 + P.shift_x - P.xoff, oy0 + P.shift_y);
+  };
+#pragma unroll 1
+  for (int i = 0; i < SW_S - 1; ++i) prefetch(i);
+  T fillv;
+  {
+    unsigned long long b = P.fill_bits;
+    memcpy(&fillv, &b, sizeof(T));
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t phase = 0;
+  const bool canon = P.bool_canon != 0, skip = P.skip_zero != 0;
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int s = i % SW_S;
+    int oy0, ox0;
+    tile_origin(i, oy0, ox0);
+    if (TMA && tid == 0 && i + SW_S - 1 < my_tiles) fence_proxy_async();
+    prefetch(i + SW_S - 1);
+    T *sm = reinterpret_cast<T *>(smem + s * P.stage_bytes);
+    const bool by_tma = async_ok(oy0, ox0);
+    if (by_tma) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      // without a tensor map, or for a tile that crosses the array's edge under a border other than Fill 0: every
+      // box cell through the border rule (Core/Index.hs:236-253); cells inside the array need no resolution
+      const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
+      const bool all_in = inside(oy0, ox0);
+      for (int r = warp; r < P.bh; r += 8) {
+        int gy = by0 + r;
+        const bool row_ok = all_in || resolve_border32(P.border, P.in_h, gy);
+        const T *srow = in + (size_t)gy * P.in_w;
+        for (int c = lane; c < P.bw; c += 32) {
+          int gx = bx0 + c;
+          T v = fillv;
+          if (row_ok && (all_in || resolve_border32(P.border, P.in_w, gx))) v = srow[gx];
+          sm[r * pitch + c] = v;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- compute: 4 x 4 outputs per thread, columns 32 apart ----
+    const T *base = sm + (warp * SW_RY) * pitch + lane;
+    T res[SW_RY][SW_CX];
+    if (P.trivial) {
+      sw_term<T>(P.X.term_kind[0], P.X.term_ntaps[0], P.X.term_avg_n[0], s_off, s_k, base, pitch, canon, skip, res);
+    } else {
+      // every term at the same index, then the postfix program over the 16 values at once (Stencil/Internal.hs:104-111)
+      T tv[MB_MAX_TERMS][SW_RY][SW_CX];
+      for (int t = 0; t < P.X.n_terms; ++t)
+        sw_term<T>(P.X.term_kind[t], P.X.term_ntaps[t], P.X.term_avg_n[t], s_off + P.X.term_begin[t], s_k + P.X.term_begin[t], base,
+                   pitch, canon, skip, tv[t]);
+      T stack[MB_MAX_STACK][SW_RY][SW_CX];
+      int sp = 0;
+      for (int k = 0; k < P.X.n_prog; ++k) {
+        const int op = P.X.op[k];
+        T cv;
+        {
+          unsigned long long b = P.X.operand[k];
+          memcpy(&cv, &b, sizeof(T));
+        }
+        if (op == MB_X_TERM) {
+          const int t = P.X.arg[k];
+#pragma unroll
+          for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) stack[sp][r][c] = tv[t][r][c];
+          ++sp;
+        } else if (op == MB_X_CONST) {
+#pragma unroll
+          for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) stack[sp][r][c] = cv;
+          ++sp;
+        } else if (op >= SW_X_POST) {
+#pragma unroll
+          for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = post_one<T>(op - SW_X_POST, stack[sp - 1][r][c], cv);
+        } else if (op <= MB_X_MAX) {
+          --sp;
+#pragma unroll
+          for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = xop_binary<T>(op, stack[sp - 1][r][c], stack[sp][r][c]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = xop_unary<T>(op, stack[sp - 1][r][c]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r)
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) res[r][c] = stack[0][r][c];
+    }
+#pragma unroll
+    for (int r = 0; r < SW_RY; ++r) {
+      const int gy = oy0 + warp * SW_RY + r;
+      if (gy < P.y1) {
+#pragma unroll
+        for (int c = 0; c < SW_CX; ++c) {
+          const int gx = ox0 + lane + 32 * c;
+          if (gx < P.out_w) out[(size_t)gy * P.out_w + gx] = res[r][c];
+        }
+      }
+    }
+    if (TMA && !by_tma) fence_proxy_async();  // generic-proxy writes into the stage come before its next TMA refill
+    __syncthreads();  // everyone is done with stage s before it is refilled
+  }
+}
+
+// the plan as (terms, program): single constructors become one term, MAG2 two terms and sqrt (a*a + b*b), post-maps
+// are appended as program steps — so that every fmap is applied in the store epilogue
+static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coef) {
+  std::memset(X, 0, sizeof(*X));
+  int n = 0;
+  auto push = [&](int op, int arg, const uint8_t *operand) {
+    X->op[n] = (unsigned char)op; X->arg[n] = (unsigned char)arg;
+    if (operand) std::memcpy(&X->operand[n], operand, 8);
+    ++n;
+  };
+  if (p.kind == MB_EXPR) {
+    X->n_terms = (int)p.terms.size();
+    for (int t = 0; t < X->n_terms; ++t) {
+      X->term_kind[t] = p.terms[t].kind; X->term_begin[t] = p.terms[t].begin;
+      X->term_ntaps[t] = p.terms[t].ntaps; X->term_avg_n[t] = p.terms[t].avg_n;
+    }
+    for (const mb_xins &x : p.prog) push(x.op, x.arg, x.operand);
+    *coef = p.c1;
+  } else if (p.kind == MB_MAG2) {
+    const int nt = (int)p.ntaps;
+    const int k = (p.flags & MB_FLAG_MAG2_CORR) ? MB_CORR : MB_CONV;
+    X->n_terms = 2;
+    X->term_kind[0] = X->term_kind[1] = k;
+    X->term_begin[0] = 0; X->term_begin[1] = nt;
+    X->term_ntaps[0] = X->term_ntaps[1] = nt;
+    coef->assign(p.c1.begin(), p.c1.end());
+    coef->insert(coef->end(), p.c2.begin(), p.c2.end());
+    // sqrt (fmap (^2) a + fmap (^2) b)  (Stencil/Internal.hs:105-146; Bench/Sobel.hs:39-44)
+    push(MB_X_TERM, 0, nullptr); push(MB_X_SQUARE, 0, nullptr); push(MB_X_TERM, 1, nullptr); push(MB_X_SQUARE, 0, nullptr);
+    push(MB_X_ADD, 0, nullptr); push(MB_X_SQRT, 0, nullptr);
+  } else {
+    switch (p.kind) {
+      case MB_ID: case MB_SUM: case MB_PRODUCT: case MB_AVG: case MB_MAX: case MB_MIN: case MB_CONV: case MB_CORR: case MB_TAPS: break;
+      default: return false;
+    }
+    X->n_terms = 1;
+    X->term_kind[0] = p.kind; X->term_begin[0] = 0; X->term_ntaps[0] = (int)p.ntaps; X->term_avg_n[0] = (int)p.avg_n;
+    push(MB_X_TERM, 0, nullptr);
+    *coef = p.c1;
+  }
+  for (const mb_post_op &q : p.post) push(SW_X_POST + q.op, 0, q.operand);
+  X->n_prog = n;
+  return true;
+}
+
+template <typename T>
+static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void *d_coef, const void *d_taps2, const void *d_in, void *d_out,
+                       const OuterRange *range) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const Plan &p = dp.p;
+  SWParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.in_h = (int)p.in_dims[0]; P.in_w = (int)p.in_dims[1];
+  P.out_h = (int)p.out_dims[0]; P.out_w = (int)p.out_dims[1];
+  P.min_dy = (int)p.min_off[0]; P.min_dx = (int)p.min_off[1];
+  P.shift_y = (int)(p.shift[0] + p.min_off[0]); P.shift_x = (int)(p.shift[1] + p.min_off[1]);
+  P.y0 = range ? (int)range->o0 : 0;
+  P.y1 = range ? (int)range->o1 : P.out_h;
+  if (P.y1 <= P.y0) return MB_OK;
+  P.tiles_x = (P.out_w + SW_TW - 1) / SW_TW;
+  P.ntiles = P.tiles_x * ((P.y1 - P.y0 + SW_TH - 1) / SW_TH);
+  P.border = p.border;
+  std::memcpy(&P.fill_bits, p.fill, 8);
+  bool fill_zero = p.border == MB_FILL;
+  for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) fill_zero = false;
+  P.zero_fill_ok = fill_zero;
+  const int wh = (int)(p.max_off[0] - p.min_off[0] + 1), ww = (int)(p.max_off[1] - p.min_off[1] + 1);
+  P.xoff = ((P.shift_x % V) + V) % V;
+  P.bw = ((P.xoff + SW_TW + ww - 1 + V - 1) / V) * V;
+  P.bh = SW_TH + wh - 1;
+  P.stage_bytes = ((P.bw * P.bh * (int)sizeof(T) + 127) / 128) * 128;
+  P.ntaps = (int)p.ntaps * (p.kind == MB_MAG2 ? 2 : 1);
+  P.bool_canon = p.elem == MB_BOOL32;
+  P.skip_zero = (p.flags & MB_FLAG_ASSUME_FINITE) != 0;
+  P.trivial = X.n_terms == 1 && X.n_prog == 1;
+  P.taps = (const int32_t *)d_taps2;
+  P.coef = d_coef;
+  P.X = X;
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  const uint32_t box[2] = {(uint32_t)P.bh, (uint32_t)P.bw};
+  P.use_tma = (!c->no_tma && P.bw <= 256 && P.bh <= 256 && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box)) ? 1 : 0;
+  const size_t smem_bytes = (size_t)SW_S * P.stage_bytes + 64 + (size_t)((P.ntaps + 3) & ~3) * 4 + (size_t)P.ntaps * sizeof(T) + 16;
+  if (smem_bytes > 200 * 1024) return -1;
+  auto kern = P.use_tma ? smallwin_kernel<T, true> : smallwin_kernel<T, false>;
+  static bool configured[64][2] = {{false}};
+  if (!configured[c->device & 63][P.use_tma]) {
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[c->device & 63][P.use_tma] = true;
+  }
+  int occ = 0;
+  MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
+  if (occ < 1) occ = 1;
+  int grid = c->num_sms * occ;
+  if (grid > P.ntiles) grid = P.ntiles;
+  kern<<<grid, 256, smem_bytes, c->stream>>>(tmap, P, (const T *)d_in, (T *)d_out);
+  c->launches++;
+  c->last_kernel = "smallwin";
+  c->post_fused = true;  // the post-maps ran as program steps
+  return check_cuda(c, cudaGetLastError(), "smallwin_kernel launch");
+}
+
+// -1: not a rank-2, unit-stride, small-window plan
+int launch_smallwin(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  const Plan &p = dp.p;
+  if (p.rank != 2 || !p.unit_stride() || p.ntaps < 1) return -1;
+  if (p.in_dims[0] < 1 || p.in_dims[1] < 1) return -1;
+  if (p.in_dims[0] >= (1ll << 30) || p.in_dims[1] >= (1ll << 30) || p.out_dims[0] >= (1ll << 30) || p.out_dims[1] >= (1ll << 30)) return -1;
+  if (p.out_elems < c->tile_min_elems) return -1;
+  if (p.max_off[0] - p.min_off[0] + 1 > SW_MAX_WIN || p.max_off[1] - p.min_off[1] + 1 > SW_MAX_WIN) return -1;
+  if (p.ntaps * (p.kind == MB_MAG2 ? 2 : 1) > SW_MAX_TAPS) return -1;
+  if (p.post.size() + p.prog.size() + 8 > sizeof(SWProgram::op)) return -1;
+  SWProgram X;
+  std::vector<uint8_t> coef;
+  if (!build_program(p, &X, &coef)) return -1;
+  // the plan's device tables as they are, except for MAG2: its two kernels share ONE tap list in the plan, the two
+  // terms here each want their own — a doubled copy is made on first use and lives with the cached plan
+  const void *d_coef = dp.d_c1;
+  const void *d_taps = dp.d_taps;
+  if (p.kind == MB_MAG2) {
+    const size_t tb = (size_t)p.ntaps * 2 * sizeof(int32_t), cb = coef.size();
+    if (!dp.d_sw) {
+      std::vector<uint8_t> host(2 * tb + cb);
+      std::memcpy(host.data(), p.tap_off.data(), tb);
+      std::memcpy(host.data() + tb, p.tap_off.data(), tb);
+      std::memcpy(host.data() + 2 * tb, coef.data(), cb);
+      MB_CUDA(c, cudaMalloc(&dp.d_sw, host.size()));
+      MB_CUDA(c, cudaMemcpy(dp.d_sw, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    d_taps = dp.d_sw;
+    d_coef = (const char *)dp.d_sw + 2 * tb;
+  }
+  switch (p.elem) {
+    case MB_U8: return launch_sw_t<uint8_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_I8: return launch_sw_t<int8_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_U16: return launch_sw_t<uint16_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_I16: return launch_sw_t<int16_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_U32: return launch_sw_t<uint32_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_I32: case MB_BOOL32: return launch_sw_t<int32_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_U64: return launch_sw_t<uint64_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_I64: return launch_sw_t<int64_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_F32: return launch_sw_t<float>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_F64: return launch_sw_t<double>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+  }
+  return -1;
+}
+
+}  // namespace mb

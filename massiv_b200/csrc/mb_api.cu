@@ -39,6 +39,7 @@ static void free_dev_plan(DevPlan *dp) {
   if (dp->d_tap_lin) cudaFree(dp->d_tap_lin);
   if (dp->d_c1) cudaFree(dp->d_c1);
   if (dp->d_c2) cudaFree(dp->d_c2);
+  if (dp->d_sw) cudaFree(dp->d_sw);
   delete dp;
 }
 
@@ -116,7 +117,7 @@ int launch_plan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const 
 // kernels would not take the slices.
 static int launch_batched(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   const Plan &p = dp.p;
-  if (p.rank < 3 || p.kind == MB_TAPS || p.kind == MB_LIFE) return -1;
+  if (p.rank < 3 || p.kind == MB_TAPS || p.kind == MB_LIFE || p.kind == MB_EXPR) return -1;
   int lead = 0;
   while (lead < p.rank && p.size[lead] == 1 && p.geom[lead] == 1 && p.stride[lead] == 1 && p.shift[lead] == 0 &&
          p.out_dims[lead] == p.in_dims[lead] && p.pad_lo[lead] == 0 && p.pad_hi[lead] == 0) ++lead;
@@ -147,6 +148,7 @@ static int launch_batched(Ctx *c, const DevPlan &dp, const void *d_in, void *d_o
     const char *in = (const char *)d_in + (size_t)b * ib;
     char *out = (char *)d_out + (size_t)b * ob;
     int st = inner == 2 ? launch_tile2d(c, *sub, in, out, nullptr) : launch_vol3d(c, *sub, in, out, nullptr);
+    if (st == -1 && inner == 2 && p.post.empty()) st = launch_smallwin(c, *sub, in, out, nullptr);
     if (st == -1) {
       if (b == b0) return -1;  // not a shape the tiled kernels cover: nothing has been launched
       st = launch_generic(c, *sub, in, out, nullptr);
@@ -167,6 +169,8 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
     st = launch_linescan(c, dp, d_in, d_out, range);
     if (st != -1) return st;
     st = launch_direct2d(c, dp, d_in, d_out, range);
+    if (st != -1) return st;
+    st = launch_smallwin(c, dp, d_in, d_out, range);
     if (st != -1) return st;
     st = launch_batched(c, dp, d_in, d_out, range);
     if (st != -1) return st;

@@ -74,6 +74,7 @@ struct DevPlan {
   int32_t *d_taps = nullptr;
   int64_t *d_tap_lin = nullptr;  // the taps as linear offsets in the input (cells whose window is inside the array)
   void *d_c1 = nullptr, *d_c2 = nullptr;
+  mutable void *d_sw = nullptr;  // small-window kernel: doubled tap list + both kernels of a MAG2 plan (made on first use)
 };
 
 struct ShardState;  // mb_shard.cu
@@ -147,6 +148,8 @@ int launch_cond_copy(Ctx *c, void *dst, const void *src, size_t bytes, const uns
 int vol3d_tb2_mode(Ctx *c, const Plan &p);
 int launch_generic(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_tile2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
+// rank 2, unit stride, any window up to 16 x 16, every kind incl. MB_TAPS / MB_EXPR, every element type (k_smallwin.cu)
+int launch_smallwin(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_vol3d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);
 int launch_life(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out);
 // Life: many generations in one go (temporal blocking); returns -1 when not applicable

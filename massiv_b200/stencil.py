@@ -100,8 +100,12 @@ class Stencil:
     scalar_size: Optional[int] = None
     along: Optional[Tuple[int, int]] = None    # (Dim, length): size 1 everywhere but along Dim (integral rules)
     post: Tuple[tuple, ...] = ()               # fmap'ed functions applied to the result, in order: (name[, c])
+    expr: Optional["_X"] = None                # kind "expr": the expression tree over base stencils (MB_EXPR)
 
     def _resolved(self, rank: int) -> "Stencil":
+        if self.kind == "expr":
+            ex = self.expr._resolved(rank)
+            return Stencil("expr", ex.size(), ex.center(), flags=self.flags, post=self.post, expr=ex)
         if self.along is not None and self.size is None:
             dim, length = self.along
             if not 1 <= dim <= rank:   # setDim' throws IndexDimensionException
@@ -128,6 +132,8 @@ class Stencil:
         constant c: "add" (+ c), "sub" (subtract c), "rsub" (c -), "mul" (* c), "div" (/ c), "rdiv" (c /), "min", "max"."""
         if name not in _abi.POSTS:
             raise NotImplementedError(f"fmap {name}: not an exactly specified post-map; closures cannot run on the device")
+        if self.kind == "expr":
+            return Stencil("expr", None, None, flags=self.flags, expr=_node_fmap(self.expr, name, c))
         if self.kind == "life" or len(self.post) >= _abi.MAX_POST:
             raise NotImplementedError("too many post-maps, or a rule stencil")
         item = (name,) if c is None else (name, c)
@@ -149,71 +155,182 @@ class Stencil:
     def sqrt(self):
         return self.fmap("sqrt")
 
-    def __add__(self, c):   # stencil + fromInteger c  ==  liftA2 (+) stencil (pure c): same size and centre
-        return self.fmap("add", c) if np.isscalar(c) else NotImplemented
+    # stencil `op` constant  ==  liftA2 op stencil (pure c): same size and centre, lowered to a post-map;
+    # stencil `op` stencil   ==  liftA2 op s1 s2 (Stencil/Internal.hs:93-131): an expression stencil (MB_EXPR)
+    def __add__(self, c):
+        return self.fmap("add", c) if np.isscalar(c) else _lift2("add", self, c)
 
-    __radd__ = __add__      # IEEE / modular addition commutes
+    def __radd__(self, c):  # IEEE / modular addition commutes
+        return self.fmap("add", c) if np.isscalar(c) else _lift2("add", c, self)
 
     def __sub__(self, c):
-        return self.fmap("sub", c) if np.isscalar(c) else NotImplemented
+        return self.fmap("sub", c) if np.isscalar(c) else _lift2("sub", self, c)
 
     def __rsub__(self, c):
-        return self.fmap("rsub", c) if np.isscalar(c) else NotImplemented
+        return self.fmap("rsub", c) if np.isscalar(c) else _lift2("sub", c, self)
 
     def __mul__(self, c):
-        return self.fmap("mul", c) if np.isscalar(c) else NotImplemented
+        return self.fmap("mul", c) if np.isscalar(c) else _lift2("mul", self, c)
 
-    __rmul__ = __mul__
+    def __rmul__(self, c):
+        return self.fmap("mul", c) if np.isscalar(c) else _lift2("mul", c, self)
 
     def __truediv__(self, c):
-        return self.fmap("div", c) if np.isscalar(c) else NotImplemented
+        return self.fmap("div", c) if np.isscalar(c) else _lift2("div", self, c)
 
     def __rtruediv__(self, c):
-        return self.fmap("rdiv", c) if np.isscalar(c) else NotImplemented
+        return self.fmap("rdiv", c) if np.isscalar(c) else _lift2("div", c, self)
 
     # Num / Floating instances (Stencil/Internal.hs:114-174) — only the Sobel-magnitude shape
     # `sqrt (fmap (^2) a + fmap (^2) b)` lowers to a device kernel (MB_MAG2).
     def __pow__(self, n):
         if n != 2:
             raise NotImplementedError("only `fmap (^2)` lowers to the device")
-        if self.kind in ("conv", "corr") and not self.post:
-            return _Squared(self)   # may still become sqrt (a^2 + b^2); resolves to fmap (^2) otherwise
         return self.fmap("square")
 
 
 @dataclass(frozen=True)
-class _Squared:
-    s: Stencil
+class _X:
+    """A node of a stencil expression: the Applicative / Num / Fractional / Floating instances of Stencil
+    (Stencil/Internal.hs:93-174) reified.  op is "term" (a built-in stencil without post-maps), "const" (`pure c`),
+    one of _abi.XOPS_BINARY (liftA2) or _abi.XOPS_UNARY (fmap)."""
+    op: str
+    args: Tuple["_X", ...] = ()
+    term: Optional[Stencil] = None
+    value: object = None
 
-    def _resolved(self, rank: int) -> "Stencil":   # used on its own: plain fmap (^2)
-        return self.s.fmap("square")._resolved(rank)
+    def _resolved(self, rank: int) -> "_X":
+        if self.op == "term":
+            return _X("term", term=self.term._resolved(rank))
+        return _X(self.op, tuple(a._resolved(rank) for a in self.args), value=self.value)
 
-    def __add__(self, other):
-        if not isinstance(other, _Squared):
-            return NotImplemented
-        return _SumSq(self.s, other.s)
+    # unionStencilCenters / unionStencilSizes (Stencil/Internal.hs:83-90); `pure` is size 1, centre 0
+    def center(self) -> Optional[Ix]:
+        if self.op == "term":
+            return _center(self.term)
+        if self.op == "const":
+            return None
+        cs = [c for c in (a.center() for a in self.args) if c is not None]
+        return tuple(max(v) for v in zip(*cs)) if cs else None
+
+    def _extent(self) -> Optional[Ix]:   # size - centre
+        if self.op == "term":
+            return tuple(g - c for g, c in zip(_geom_size(self.term), _center(self.term)))
+        if self.op == "const":
+            return None
+        es = [e for e in (a._extent() for a in self.args) if e is not None]
+        return tuple(max(max(v), 1) for v in zip(*es)) if es else None
+
+    def size(self) -> Optional[Ix]:
+        c, e = self.center(), self._extent()
+        return None if c is None else tuple(a + b for a, b in zip(c, e))
 
 
-@dataclass(frozen=True)
-class _SumSq:
-    a: Stencil
-    b: Stencil
+def _term_node(st: Stencil) -> _X:
+    """a stencil as an expression node: its post-maps become fmap / liftA2-with-pure nodes"""
+    if st.kind == "expr":
+        return st.expr
+    if st.kind in ("life", "mag2") or st.kind.startswith("int_"):
+        raise NotImplementedError(f"{st.kind} stencils do not combine into expressions")
+    node = _X("term", term=Stencil(st.kind, st.size, st.center, st.coeffs, None, st.taps, 0, st.scalar_size, st.along))
+    for item in st.post:
+        node = _node_fmap(node, item[0], item[1] if len(item) > 1 else None)
+    return node
 
 
-def sqrt(x):
-    """``sqrt`` of the Floating (Stencil ix e) instance: ``sqrt(sx**2 + sy**2)`` fuses into one kernel
-    (MB_MAG2); ``sqrt stencil`` is ``fmap sqrt``."""
+def _node_fmap(node: _X, name: str, c=None) -> _X:
+    if name in _abi.XOPS_UNARY:
+        return _X(name, (node,))
+    if name in _abi.XOPS_BINARY:            # (`op` c)
+        return _X(name, (node, _X("const", value=c)))
+    if name == "rsub":                      # (c -)
+        return _X("sub", (_X("const", value=c), node))
+    if name == "rdiv":                      # (c /)
+        return _X("div", (_X("const", value=c), node))
+    raise NotImplementedError(f"fmap {name}")
+
+
+def _as_node(x) -> _X:
     if isinstance(x, Stencil):
-        return x.fmap("sqrt")
-    if isinstance(x, _Squared):
-        return x.s.fmap("square").fmap("sqrt")
-    if not isinstance(x, _SumSq):
-        raise NotImplementedError("only sqrt(a**2 + b**2) of two FromKernel stencils lowers to the device")
-    a, b = x.a, x.b
-    if a.kind != b.kind or a.size != b.size:
-        raise NotImplementedError("MAG2 needs two stencils from one constructor and of one size")
-    flags = (a.flags | b.flags) | (_abi.FLAG_MAG2_CORR if a.kind == "corr" else 0)
-    return Stencil("mag2", a.size, None, a.coeffs, b.coeffs, None, flags)
+        return _term_node(x)
+    if isinstance(x, _X):
+        return x
+    raise TypeError(f"cannot combine a stencil with {type(x).__name__}")
+
+
+def _lift2(op: str, a, b) -> Stencil:
+    """``liftA2 op a b`` of two stencils (Stencil/Internal.hs:104-111): one pass, an MB_EXPR descriptor"""
+    if not isinstance(a, Stencil) or not isinstance(b, Stencil):
+        return NotImplemented
+    flags = (a.flags | b.flags) & _abi.FLAG_ASSUME_FINITE
+    return Stencil("expr", None, None, flags=flags, expr=_X(op, (_as_node(a), _as_node(b))))
+
+
+def minStencils(a: Stencil, b: Stencil) -> Stencil:
+    """``liftA2 min a b``"""
+    return _lift2("min", a, b)
+
+
+def maxStencils(a: Stencil, b: Stencil) -> Stencil:
+    """``liftA2 max a b``"""
+    return _lift2("max", a, b)
+
+
+def _squared_kernel(node: _X) -> Optional[Stencil]:
+    """the FromKernel stencil k when node is ``fmap (^2) k`` or ``k * k``"""
+    if node.op == "square" and node.args[0].op == "term":
+        t = node.args[0].term
+    elif node.op == "mul" and node.args[0].op == "term" and node.args[1].op == "term" and node.args[0].term is node.args[1].term:
+        t = node.args[0].term
+    else:
+        return None
+    return t if t.kind in ("conv", "corr") and t.size is not None else None
+
+
+def sqrt(x: Stencil) -> Stencil:
+    """``sqrt`` of the Floating (Stencil ix e) instance: ``fmap sqrt``.  The Sobel-magnitude shape
+    ``sqrt (fmap (^2) a + fmap (^2) b)`` of two FromKernel stencils of one size takes the dedicated MB_MAG2 kernels;
+    every other expression is evaluated as MB_EXPR."""
+    if not isinstance(x, Stencil):
+        raise NotImplementedError("sqrt of this object does not lower to the device")
+    if x.kind == "expr" and x.expr.op == "add":
+        a, b = _squared_kernel(x.expr.args[0]), _squared_kernel(x.expr.args[1])
+        if a is not None and b is not None and a.kind == b.kind and a.size == b.size:
+            flags = x.flags | (_abi.FLAG_MAG2_CORR if a.kind == "corr" else 0)
+            return Stencil("mag2", a.size, None, a.coeffs, b.coeffs, None, flags)
+    return x.fmap("sqrt")
+
+
+def _flatten(node: _X, rank: int):
+    """expression tree -> (distinct term stencils, postfix program [(op, arg)]) within the descriptor's limits"""
+    terms, prog = [], []
+
+    def key(t: Stencil):
+        return (t.kind, t.size, t.center, None if t.coeffs is None else np.asarray(t.coeffs).tobytes(),
+                None if t.coeffs is None else str(np.asarray(t.coeffs).dtype), t.taps)
+
+    keys = []
+
+    def walk(n: _X) -> int:   # returns the stack depth the subtree needs
+        if n.op == "term":
+            k = key(n.term)
+            if k not in keys:
+                keys.append(k)
+                terms.append(n.term)
+            prog.append(("term", keys.index(k)))
+            return 1
+        if n.op == "const":
+            prog.append(("const", n.value))
+            return 1
+        depths = [walk(a) for a in n.args]
+        prog.append((n.op, None))
+        return max(d + i for i, d in enumerate(depths))
+
+    depth = walk(node)
+    if len(terms) > _abi.MAX_TERMS or len(prog) > _abi.MAX_PROGRAM or depth > _abi.MAX_STACK:
+        raise NotImplementedError(f"stencil expression too large for one descriptor: {len(terms)} terms, {len(prog)} steps, "
+                                  f"stack {depth} (limits {_abi.MAX_TERMS}, {_abi.MAX_PROGRAM}, {_abi.MAX_STACK})")
+    return terms, prog
 
 
 def getStencilSize(st: Stencil) -> Ix:
@@ -225,6 +342,8 @@ def getStencilCenter(st: Stencil) -> Ix:
 
 
 def _geom_size(st: Stencil) -> Ix:
+    if st.kind == "expr":
+        return st.size if st.size is not None else st.expr.size()
     if st.kind == "avg":   # liftA2 (/) with `pure n`: unionStencilSizes (Stencil/Internal.hs:83-90)
         return tuple(max(s, 1) for s in st.size)
     return st.size
@@ -233,6 +352,8 @@ def _geom_size(st: Stencil) -> Ix:
 def _center(st: Stencil) -> Ix:
     if st.center is not None:
         return st.center
+    if st.kind == "expr":
+        return st.expr.center()
     if st.kind == "conv" or (st.kind == "mag2" and not st.flags & _abi.FLAG_MAG2_CORR):
         return tuple(s - 1 - s // 2 for s in st.size)    # Convolution.hs:71-73
     if st.kind in ("corr", "mag2"):
@@ -516,6 +637,33 @@ class DW:
             keep.append(offs)
             d.ntaps, d.tap_offsets = offs.shape[0], offs.ctypes.data
         d.flags = st.flags
+        if st.kind == "expr":
+            terms, prog = _flatten(st.expr, rank)
+            ta = (_abi.Term * len(terms))()
+            for i, t in enumerate(terms):
+                ta[i].kind = _abi.KINDS[t.kind]
+                tc = _center(t)
+                for j in range(rank):
+                    ta[i].size[j], ta[i].center[j] = t.size[j], tc[j]
+                if t.coeffs is not None:
+                    kk = np.ascontiguousarray(np.asarray(t.coeffs).astype(npdt)).reshape(-1)
+                    keep.append(kk)
+                    ta[i].coeffs = kk.ctypes.data
+                if t.taps is not None:
+                    offs = np.ascontiguousarray(np.asarray(t.taps, dtype=np.int64).reshape(-1, rank))
+                    keep.append(offs)
+                    ta[i].ntaps, ta[i].tap_offsets = offs.shape[0], offs.ctypes.data
+            pa = (_abi.XIns * len(prog))()
+            for i, (op, arg) in enumerate(prog):
+                pa[i].op = _abi.XOPS[op]
+                if op == "term":
+                    pa[i].arg = arg
+                elif op == "const":
+                    for j, byte in enumerate(np.array([arg]).astype(npdt).tobytes()):
+                        pa[i].operand[j] = byte
+            keep += [ta, pa]
+            d.n_terms, d.n_program = len(terms), len(prog)
+            d.terms, d.program = C.cast(ta, C.c_void_p), C.cast(pa, C.c_void_p)
         if st.post:
             pa = _abi.post_array(st.post, npdt)
             keep.append(pa)

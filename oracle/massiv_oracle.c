@@ -104,14 +104,74 @@ static int validate(const mo_desc *d) {
       if (d->kind == MO_INT_SIMPSON && (len < 3 || (len - 1) % 2 != 0)) return MO_ERR_UNSUPPORTED;
       break;
     }
+    case MO_EXPR: {
+      if (d->elem == MO_BOOL32) return MO_ERR_UNSUPPORTED;
+      if (d->n_terms < 1 || d->n_terms > MO_MAX_TERMS || !d->terms) return MO_ERR_INVALID_DESC;
+      if (d->n_program < 1 || d->n_program > MO_MAX_PROGRAM || !d->program) return MO_ERR_INVALID_DESC;
+      for (uint32_t t = 0; t < d->n_terms; ++t) {
+        mo_desc td = *d; /* same element type, rank, border; the term's own constructor arguments */
+        td.kind = d->terms[t].kind;
+        if (td.kind < MO_ID || td.kind > MO_TAPS) return MO_ERR_UNSUPPORTED;
+        td.coeffs = d->terms[t].coeffs; td.coeffs2 = NULL; td.ntaps = d->terms[t].ntaps; td.tap_offsets = d->terms[t].tap_offsets;
+        for (int i = 0; i < d->rank; ++i) {
+          td.size[i] = d->terms[t].size[i];
+          if (td.size[i] < 1) return MO_ERR_UNSUPPORTED;
+        }
+        int st = validate(&td);
+        if (st) return st;
+      }
+      int depth = 0;
+      for (uint32_t i = 0; i < d->n_program; ++i) {
+        const int op = d->program[i].op;
+        if (op == MO_X_TERM) { if (d->program[i].arg < 0 || (uint32_t)d->program[i].arg >= d->n_terms) return MO_ERR_INVALID_DESC; ++depth; }
+        else if (op == MO_X_CONST) ++depth;
+        else if (op >= MO_X_ADD && op <= MO_X_MAX) { if (op == MO_X_DIV && !is_float(d->elem)) return MO_ERR_UNSUPPORTED; if (depth < 2) return MO_ERR_INVALID_DESC; --depth; }
+        else if (op >= MO_X_NEGATE && op <= MO_X_SQRT) { if (op >= MO_X_RECIP && !is_float(d->elem)) return MO_ERR_UNSUPPORTED; if (depth < 1) return MO_ERR_INVALID_DESC; }
+        else return MO_ERR_INVALID_DESC;
+        if (depth > MO_MAX_STACK) return MO_ERR_UNSUPPORTED;
+      }
+      if (depth != 1) return MO_ERR_INVALID_DESC;
+      break;
+    }
     default: return MO_ERR_INVALID_DESC;
   }
   return MO_OK;
 }
 
+/* geometry (size used for the output-size arithmetic) and stencilCenter of one constructor, one dimension */
+static void kind_geom(int32_t kind, uint32_t flags, int64_t s, int64_t given, int64_t *g, int64_t *c) {
+  *g = s; *c = 0;
+  switch (kind) {
+    case MO_AVG: *g = s > 1 ? s : 1; break;
+    case MO_CONV: *c = s - 1 - s / 2; break;
+    case MO_MAG2: *c = (flags & MO_FLAG_MAG2_CORR) ? floor_div(s, 2) : s - 1 - s / 2; break;
+    case MO_CORR: *c = floor_div(s, 2); break;
+    case MO_TAPS: *c = given; break;
+    case MO_LIFE: *g = 3; *c = 1; break;
+    default: break;
+  }
+}
+
 int mo_geom(const mo_desc *d, int64_t *g, int64_t *c) {
   int st = validate(d);
   if (st) return st;
+  if (d->kind == MO_EXPR) {
+    /* unionStencilCenters: max of the centres; unionStencilSizes: centre + max (size - centre)
+     * (Stencil/Internal.hs:83-90), folded over all terms; `pure c` is size 1, centre 0 */
+    for (int i = 0; i < d->rank; ++i) {
+      int64_t mc = 0, ext = 1;
+      for (uint32_t t = 0; t < d->n_terms; ++t) {
+        int64_t tg, tc;
+        kind_geom(d->terms[t].kind, 0, d->terms[t].size[i], d->terms[t].center[i], &tg, &tc);
+        if (d->terms[t].center[i] != tc) return MO_ERR_INVALID_DESC;
+        if (tc > mc) mc = tc;
+        if (tg - tc > ext) ext = tg - tc;
+      }
+      c[i] = mc; g[i] = mc + ext;
+      if (d->center[i] != c[i] || d->size[i] != g[i]) return MO_ERR_INVALID_DESC;
+    }
+    return MO_OK;
+  }
   for (int i = 0; i < d->rank; ++i) {
     int64_t s = d->size[i];
     switch (d->kind) {
@@ -418,11 +478,95 @@ static int apply_post(const mo_desc *d, void *out, int64_t n) {
   return MO_OK;
 }
 
+static void run_plan(int32_t elem, mo_plan *p, const void *in, void *out, int nthreads) {
+  switch (elem) {
+    case MO_U8: apply_u8(p, (const uint8_t *)in, (uint8_t *)out, nthreads); break;
+    case MO_I8: apply_i8(p, (const int8_t *)in, (int8_t *)out, nthreads); break;
+    case MO_U16: apply_u16(p, (const uint16_t *)in, (uint16_t *)out, nthreads); break;
+    case MO_I16: apply_i16(p, (const int16_t *)in, (int16_t *)out, nthreads); break;
+    case MO_U32: apply_u32(p, (const uint32_t *)in, (uint32_t *)out, nthreads); break;
+    case MO_I32: apply_i32(p, (const int32_t *)in, (int32_t *)out, nthreads); break;
+    case MO_U64: apply_u64(p, (const uint64_t *)in, (uint64_t *)out, nthreads); break;
+    case MO_I64: apply_i64(p, (const int64_t *)in, (int64_t *)out, nthreads); break;
+    case MO_BOOL32: apply_b32(p, (const int32_t *)in, (int32_t *)out, nthreads); break;
+    case MO_F32: apply_f32(p, (const float *)in, (float *)out, nthreads); break;
+    default: apply_f64(p, (const double *)in, (double *)out, nthreads); break;
+  }
+}
+
+/* MO_EXPR (Stencil/Internal.hs:93-174): every term is evaluated over the whole output at the SAME absolute
+ * source index — output cell o sits at o + (centre - pad_lo) with the UNION centre (Stencil.hs:200) — into
+ * an array of its own; the postfix program then combines the arrays cell by cell in the element type.
+ * The reference composes the closures per cell instead; the values are the same (each f_t is a pure function
+ * of the index).  liftA2 min / max use GHC.Classes' defaults (min x y = if x <= y then x else y). */
+static int apply_expr(const mo_desc *d, const int64_t *in_dims, const void *in, void *out, int nthreads) {
+  int64_t g[MO_MAX_RANK], c[MO_MAX_RANK], od[MO_MAX_RANK];
+  int st = mo_geom(d, g, c);
+  if (st) return st;
+  if ((st = mo_out_dims(d, in_dims, od))) return st;
+  const int r = d->rank;
+  const int es = mo_elem_size(d->elem);
+  int64_t n = 1; int zero_in = 0;
+  for (int i = 0; i < r; ++i) { n *= od[i]; if (in_dims[i] == 0) zero_in = 1; }
+  void *tv[MO_MAX_TERMS] = {0};
+  for (uint32_t t = 0; t < d->n_terms && !st; ++t) {
+    mo_desc td = *d;
+    td.kind = d->terms[t].kind; td.coeffs = d->terms[t].coeffs; td.coeffs2 = NULL;
+    td.ntaps = d->terms[t].ntaps; td.tap_offsets = d->terms[t].tap_offsets;
+    td.n_post = 0; td.n_terms = 0; td.n_program = 0; td.flags = d->flags & MO_FLAG_NO_FAST;
+    for (int i = 0; i < r; ++i) {
+      td.size[i] = d->terms[t].size[i]; td.center[i] = d->terms[t].center[i];
+      td.pad_lo[i] = 0; td.pad_hi[i] = 0;
+    }
+    mo_plan p;
+    if ((st = build_plan(&td, in_dims, &p))) break;
+    for (int i = 0; i < r; ++i) { p.shift[i] = c[i] - d->pad_lo[i]; p.out_dims[i] = od[i]; }
+    if (n > 0 && p.ntaps > 0 && zero_in && d->border != MO_FILL) { free_plan(&p); st = MO_ERR_INDEX_ZERO; break; }
+    tv[t] = malloc((size_t)(n > 0 ? n : 1) * es);
+    if (n > 0) run_plan(d->elem, &p, in, tv[t], nthreads);
+    free_plan(&p);
+  }
+  if (!st) {
+    static const int un_map[] = {MO_POST_NEGATE, MO_POST_ABS, MO_POST_SIGNUM, MO_POST_SQUARE, MO_POST_RECIP, MO_POST_SQRT};
+    static const int bin_map[] = {MO_POST_ADD, MO_POST_SUB, MO_POST_MUL, MO_POST_DIV, MO_POST_MIN, MO_POST_MAX};
+#define RUNX(T, F)                                                                             \
+    for (int64_t i = 0; i < n; ++i) {                                                          \
+      T stack[MO_MAX_STACK]; int sp = 0;                                                       \
+      for (uint32_t k = 0; k < d->n_program; ++k) {                                            \
+        const mo_xins *x = &d->program[k];                                                     \
+        if (x->op == MO_X_TERM) stack[sp++] = ((const T *)tv[x->arg])[i];                      \
+        else if (x->op == MO_X_CONST) { T cv; memcpy(&cv, x->operand, sizeof(T)); stack[sp++] = cv; } \
+        else if (x->op <= MO_X_MAX) { T b = stack[--sp]; T a = stack[sp - 1]; stack[sp - 1] = F(bin_map[x->op - MO_X_ADD], a, b); } \
+        else stack[sp - 1] = F(un_map[x->op - MO_X_NEGATE], stack[sp - 1], (T)0);              \
+      }                                                                                        \
+      ((T *)out)[i] = stack[0];                                                                \
+    }
+    switch (d->elem) {
+      case MO_U8: RUNX(uint8_t, post_u8) break;
+      case MO_I8: RUNX(int8_t, post_i8) break;
+      case MO_U16: RUNX(uint16_t, post_u16) break;
+      case MO_I16: RUNX(int16_t, post_i16) break;
+      case MO_U32: RUNX(uint32_t, post_u32) break;
+      case MO_I32: RUNX(int32_t, post_i32) break;
+      case MO_U64: RUNX(uint64_t, post_u64) break;
+      case MO_I64: RUNX(int64_t, post_i64) break;
+      case MO_F32: RUNX(float, post_f32) break;
+      case MO_F64: RUNX(double, post_f64) break;
+      default: st = MO_ERR_UNSUPPORTED;
+    }
+#undef RUNX
+  }
+  for (uint32_t t = 0; t < d->n_terms; ++t) free(tv[t]);
+  if (!st && d->n_post) st = apply_post(d, out, n);
+  return st;
+}
+
 int mo_apply(const mo_desc *d, const int64_t *in_dims, const void *in, void *out, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (d->kind == MO_EXPR) return apply_expr(d, in_dims, in, out, nthreads);
   mo_plan p;
   int st = build_plan(d, in_dims, &p);
   if (st) return st;
-  if (nthreads < 1) nthreads = 1;
   switch (d->elem) {
     case MO_U8: apply_u8(&p, (const uint8_t *)in, (uint8_t *)out, nthreads); break;
     case MO_I8: apply_i8(&p, (const int8_t *)in, (int8_t *)out, nthreads); break;

@@ -53,8 +53,27 @@ enum { MO_ID = 0,      /* idStencil                                  Stencil.hs:
        /* Integral approximation rules: 1-D along one dimension, centre 0, coeffs[0] = dx  */
        MO_INT_MIDPOINT,  /* midpointStencil                          Numeric/Integral.hs:54-66   */
        MO_INT_TRAPEZOID, /* trapezoidStencil                         Numeric/Integral.hs:75-90   */
-       MO_INT_SIMPSON    /* simpsonsStencil (n even)                 Numeric/Integral.hs:99-118  */
+       MO_INT_SIMPSON,   /* simpsonsStencil (n even)                 Numeric/Integral.hs:99-118  */
+       MO_EXPR           /* Applicative / Num / Fractional / Floating instances of Stencil: terms (sub-stencils of
+                            kinds MO_ID..MO_TAPS) combined point-wise by a postfix program; size / centre are the
+                            unions of Stencil/Internal.hs:83-90                     Stencil/Internal.hs:93-174  */
 };
+
+/* MO_EXPR: a term is a sub-stencil evaluated at the SAME absolute source index as every other term
+ * (stF ug gV ix = f (f1 ug gV ix) (f2 ug gV ix), Internal.hs:104-111) */
+typedef struct mo_term {
+  int32_t kind, reserved;
+  int64_t size[MO_MAX_RANK], center[MO_MAX_RANK];
+  const void *coeffs;
+  int64_t ntaps;
+  const int64_t *tap_offsets;
+} mo_term;
+enum { MO_X_TERM = 1, MO_X_CONST, MO_X_ADD, MO_X_SUB, MO_X_MUL, MO_X_DIV, MO_X_MIN, MO_X_MAX, MO_X_NEGATE, MO_X_ABS,
+       MO_X_SIGNUM, MO_X_SQUARE, MO_X_RECIP, MO_X_SQRT };
+typedef struct mo_xins { int32_t op, arg; uint8_t operand[8]; } mo_xins;
+#define MO_MAX_TERMS 8
+#define MO_MAX_PROGRAM 32
+#define MO_MAX_STACK 8
 
 enum { MO_FILL = 0, MO_WRAP, MO_EDGE, MO_REFLECT, MO_CONTINUE };
 
@@ -87,6 +106,9 @@ typedef struct mo_desc {
   uint32_t flags;
   uint32_t n_post;               /* post-maps (fmap f over the results), applied in order        */
   const struct mo_post_op *post;
+  uint32_t n_terms, n_program;   /* MO_EXPR                                                       */
+  const mo_term *terms;
+  const mo_xins *program;
 } mo_desc;
 
 /* repaired index of handleBorderIndex for one dimension; *fill set to 1 when a Fill border

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "libmassiv_oracle.so")
 MAX_RANK = 5
 
 KINDS = {"id": 0, "sum": 1, "product": 2, "avg": 3, "max": 4, "min": 5, "conv": 6, "corr": 7,
-         "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13}
+         "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13, "expr": 14}
 BORDERS = {"fill": 0, "wrap": 1, "edge": 2, "reflect": 3, "continue": 4}
 ELEMS = {"u8": 0, "i8": 1, "u16": 2, "i16": 3, "u32": 4, "i32": 5, "u64": 6, "i64": 7,
          "f32": 8, "f64": 9, "bool32": 10}
@@ -72,7 +72,21 @@ class _Desc(C.Structure):
                 ("pad_lo", C.c_int64 * MAX_RANK), ("pad_hi", C.c_int64 * MAX_RANK),
                 ("stride", C.c_int64 * MAX_RANK), ("fill", C.c_uint8 * 8),
                 ("coeffs", C.c_void_p), ("coeffs2", C.c_void_p), ("ntaps", C.c_int64),
-                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p)]
+                ("tap_offsets", C.c_void_p), ("flags", C.c_uint32), ("n_post", C.c_uint32), ("post", C.c_void_p),
+                ("n_terms", C.c_uint32), ("n_program", C.c_uint32), ("terms", C.c_void_p), ("program", C.c_void_p)]
+
+
+class _Term(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("size", C.c_int64 * MAX_RANK), ("center", C.c_int64 * MAX_RANK),
+                ("coeffs", C.c_void_p), ("ntaps", C.c_int64), ("tap_offsets", C.c_void_p)]
+
+
+class _XIns(C.Structure):
+    _fields_ = [("op", C.c_int32), ("arg", C.c_int32), ("operand", C.c_uint8 * 8)]
+
+
+XOPS = {"term": 1, "const": 2, "add": 3, "sub": 4, "mul": 5, "div": 6, "min": 7, "max": 8, "negate": 9, "abs": 10,
+        "signum": 11, "square": 12, "recip": 13, "sqrt": 14}
 
 
 def build(force: bool = False) -> str:
@@ -133,11 +147,27 @@ class _Built:
         self.desc, self.keep = desc, keep
 
 
-def make_desc(kind: str, elem: str, rank: int, *, size, center=None, pad_lo=None, pad_hi=None,
+def expr_geom(terms, rank: int):
+    """(size, centre) of an expression: unionStencilCenters / unionStencilSizes over its terms
+    (Stencil/Internal.hs:83-90); terms are dicts(kind=, size=[, center=, coeffs=, taps=])"""
+    cs = [t.get("center") or expected_center(t["kind"], t["size"]) for t in terms]
+    gs = [geom_size(t["kind"], t["size"]) for t in terms]
+    mc = tuple(max(c[i] for c in cs) for i in range(rank))
+    ext = tuple(max(max(g[i] - c[i] for g, c in zip(gs, cs)), 1) for i in range(rank))
+    return tuple(a + b for a, b in zip(mc, ext)), mc
+
+
+def make_desc(kind: str, elem: str, rank: int, *, size=None, center=None, pad_lo=None, pad_hi=None,
               border="fill", fill=0, stride=None, coeffs=None, coeffs2=None, taps=None,
-              flags: int = 0, post=None) -> _Built:
+              flags: int = 0, post=None, terms=None, program=None) -> _Built:
+    """kind "expr": terms = [dict(kind=, size=[, center=, coeffs=, taps=])], program = [("term", i) | ("const", c) |
+    (op,)] in postfix order; size / centre default to the union of the terms'"""
     d = _Desc()
     keep = []
+    if kind == "expr":
+        usz, uc = expr_geom(terms, rank)
+        size = usz if size is None else size
+        center = uc if center is None else center
     d.kind, d.elem, d.rank, d.border = KINDS[kind], ELEMS[elem], rank, BORDERS[border]
     size = tuple(int(s) for s in size)
     assert len(size) == rank
@@ -174,6 +204,33 @@ def make_desc(kind: str, elem: str, rank: int, *, size, center=None, pad_lo=None
         pa = post_array(post, npdt)
         keep.append(pa)
         d.n_post, d.post = len(post), C.cast(pa, C.c_void_p)
+    if kind == "expr":
+        ta = (_Term * len(terms))()
+        for i, t in enumerate(terms):
+            ta[i].kind = KINDS[t["kind"]]
+            tsz = tuple(int(v) for v in t["size"])
+            tc = t.get("center") or expected_center(t["kind"], tsz)
+            for j in range(rank):
+                ta[i].size[j], ta[i].center[j] = tsz[j], int(tc[j])
+            if t.get("coeffs") is not None:
+                kk = np.ascontiguousarray(np.asarray(t["coeffs"]).astype(npdt)).reshape(-1)
+                keep.append(kk)
+                ta[i].coeffs = kk.ctypes.data
+            if t.get("taps") is not None:
+                offs = np.ascontiguousarray(np.asarray(t["taps"], dtype=np.int64).reshape(-1, rank))
+                keep.append(offs)
+                ta[i].ntaps, ta[i].tap_offsets = offs.shape[0], offs.ctypes.data
+        xa = (_XIns * len(program))()
+        for i, step in enumerate(program):
+            xa[i].op = XOPS[step[0]]
+            if step[0] == "term":
+                xa[i].arg = int(step[1])
+            elif step[0] == "const":
+                for j, b in enumerate(np.array([step[1]]).astype(npdt).tobytes()):
+                    xa[i].operand[j] = b
+        keep += [ta, xa]
+        d.n_terms, d.n_program = len(terms), len(program)
+        d.terms, d.program = C.cast(ta, C.c_void_p), C.cast(xa, C.c_void_p)
     return _Built(d, keep)
 
 

@@ -128,5 +128,6 @@ def test_sobel_magnitude_lowers_to_mag2():
     sx, sy = M.makeConvolutionStencilFromKernel(kx), M.makeConvolutionStencilFromKernel(kx.T)
     op = M.sqrt(sx ** 2 + sy ** 2)
     assert op.kind == "mag2" and op.size == (3, 3) and M.getStencilCenter(op) == (1, 1)
-    with pytest.raises(NotImplementedError):
-        M.sqrt(sx ** 2 + M.makeConvolutionStencilFromKernel(np.ones((5, 5), np.float32)) ** 2)
+    # kernels of different sizes: no MAG2 kernel, but still one pass — an expression stencil with the union geometry
+    op2 = M.sqrt(sx ** 2 + M.makeConvolutionStencilFromKernel(np.ones((5, 5), np.float32)) ** 2)._resolved(2)
+    assert op2.kind == "expr" and op2.size == (5, 5) and M.getStencilCenter(op2) == (2, 2)

@@ -16,8 +16,11 @@ NEEDS_C = {"add", "sub", "rsub", "mul", "min", "max", "div", "rdiv"}
 
 
 def test_struct_layout():
-    assert C.sizeof(_abi.StencilDesc) == 272 == C.sizeof(O._Desc)
+    assert C.sizeof(_abi.StencilDesc) == 296 == C.sizeof(O._Desc)
     assert _abi.StencilDesc.n_post.offset == 260 and _abi.StencilDesc.post.offset == 264
+    assert (_abi.StencilDesc.n_terms.offset, _abi.StencilDesc.n_program.offset, _abi.StencilDesc.terms.offset,
+            _abi.StencilDesc.program.offset) == (272, 276, 280, 288)
+    assert C.sizeof(_abi.Term) == 112 == C.sizeof(O._Term) and C.sizeof(_abi.XIns) == 16 == C.sizeof(O._XIns)
     assert C.sizeof(_abi.PostOp) == 16
 
 
