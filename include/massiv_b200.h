@@ -267,6 +267,22 @@ int mb_iterate_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims
 int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in,
                void *host_out, int64_t n_steps);
 
+/* iterateUntil with a convergence predicate (Manifest/Internal.hs:331-349).  The reference's predicate is a closure
+ * over the step number and the last two arrays; the device path evaluates the two predicates its users write:
+ *   MB_UNTIL_EQUAL         cur == prev element-wise (Eq e: NaN /= NaN, -0 == 0): a fixed point, e.g. a Life board of
+ *                          still lifes
+ *   MB_UNTIL_MAX_ABS_DIFF  maximum |cur - prev| < tol (Float / Double; a NaN difference never converges)
+ * after every `check_every`-th application (1: after every step, exactly iterateUntil; k > 1 is the predicate
+ * `\n p c -> (n + 1) `mod` k == 0 && pred p c`), and gives up after max_steps applications.  The reduction runs on
+ * the device; only its verdict travels to the host.  *steps receives the number of applications made, *converged
+ * whether the predicate held, *result (device form) the buffer that holds the last array. */
+typedef enum mb_until { MB_UNTIL_EQUAL = 0, MB_UNTIL_MAX_ABS_DIFF = 1 } mb_until;
+int mb_iterate_until_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, void *dev_a, void *dev_b,
+                         int64_t max_steps, int64_t check_every, int predicate, double tol, int64_t *steps,
+                         int32_t *converged, void **result);
+int mb_iterate_until(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in, void *host_out,
+                     int64_t max_steps, int64_t check_every, int predicate, double tol, int64_t *steps, int32_t *converged);
+
 /* ---- slab-sharded iteration across the GPUs of one box (one process per GPU) ---------------- */
 /* The global array is split along dims[0] into contiguous slabs, rank r owning planes
  * [r*N/R, (r+1)*N/R).  Every round (one step, or two fused steps for star-shaped 3-D kernels under

@@ -7,7 +7,7 @@ from ._abi import (IndexZeroException, MassivB200Error, SizeMismatchException)  
 from .stencil import (  # noqa: F401
     Border, Continue, DW, Device, DeviceArray, Edge, Fill, Padding, Reflect, Stencil, Sz, Wrap,
     applyStencil, avgStencil, compute, computeInto, computeSeparable, computeWithStride,
-    getStencilCenter, getStencilSize, handleBorderIndex, idStencil, iterateStencil, lifeStencil,
+    getStencilCenter, getStencilSize, handleBorderIndex, idStencil, iterateStencil, iterateUntil, lifeStencil,
     makeConvolutionStencil, makeConvolutionStencilFromKernel, makeCorrelationStencil,
     makeCorrelationStencilFromKernel, makeUnsafeConvolutionStencil, makeUnsafeCorrelationStencil,
     mapStencil, maxStencil, maxStencils, minStencil, minStencils, noPadding, productStencil, samePadding, sqrt, sumStencil,

@@ -23,6 +23,7 @@ KINDS = {"id": 0, "sum": 1, "product": 2, "avg": 3, "max": 4, "min": 5, "conv": 
          "taps": 8, "life": 9, "mag2": 10, "int_midpoint": 11, "int_trapezoid": 12, "int_simpson": 13, "expr": 14}
 BORDERS = {"fill": 0, "wrap": 1, "edge": 2, "reflect": 3, "continue": 4}
 FLAG_MAG2_CORR = 1
+UNTIL_EQUAL, UNTIL_MAX_ABS_DIFF = 0, 1
 FLAG_ASSUME_FINITE = 2
 
 # every symbol include/massiv_b200.h declares (tests check the .so exports all of them)
@@ -32,7 +33,7 @@ SYMBOLS = [
     "mb_elem_size", "mb_out_dims", "mb_border_index", "mb_buf_alloc", "mb_buf_free", "mb_upload",
     "mb_download", "mb_host_alloc", "mb_host_free", "mb_run", "mb_run_dev", "mb_run_sep2_dev",
     "mb_run_sep2", "mb_iterate_dev", "mb_iterate", "mb_nccl_unique_id", "mb_shard_init",
-    "mb_shard_halo", "mb_shard_plan_make", "mb_iterate_sharded_dev", "mb_iterate_sharded", "mb_shard_transport", "mb_timer_start", "mb_timer_stop", "mb_selftest_div", "mb_compare_dev",
+    "mb_shard_halo", "mb_shard_plan_make", "mb_iterate_sharded_dev", "mb_iterate_sharded", "mb_shard_transport", "mb_timer_start", "mb_timer_stop", "mb_selftest_div", "mb_compare_dev", "mb_iterate_until_dev", "mb_iterate_until",
 ]
 
 
@@ -173,6 +174,9 @@ def lib() -> C.CDLL:
     L.mb_shard_transport.argtypes = [vp]
     L.mb_selftest_div.argtypes = [vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64)]
+    L.mb_iterate_until_dev.argtypes = [vp, dp, i64p, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_double, i64p, C.POINTER(C.c_int32),
+                                       C.POINTER(vp)]
+    L.mb_iterate_until.argtypes = [vp, dp, i64p, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_double, i64p, C.POINTER(C.c_int32)]
     L.mb_compare_dev.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.mb_timer_start.argtypes = [vp]
     L.mb_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]

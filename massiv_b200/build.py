@@ -21,7 +21,7 @@ OBJ = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libmassiv_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 SOURCES = ["mb_plan.cpp", "mb_api.cu", "k_generic.cu", "k_tile2d.cu", "k_vol3d.cu", "k_life.cu", "mb_shard.cu",
-           "k_selftest.cu", "k_sep2d.cu", "k_tile2d_known.cu", "k_vol3d_tb2.cu", "k_linescan.cu", "k_direct2d.cu", "k_post.cu", "k_smallwin.cu"]
+           "k_selftest.cu", "k_sep2d.cu", "k_tile2d_known.cu", "k_vol3d_tb2.cu", "k_linescan.cu", "k_direct2d.cu", "k_post.cu", "k_smallwin.cu", "k_converge.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: belt and braces — the kernels already use explicit *_rn intrinsics, which nvcc
 # never contracts; explicit fma() calls (exact-division helper) are unaffected by the flag.

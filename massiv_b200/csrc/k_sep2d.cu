@@ -17,6 +17,7 @@ namespace mb {
 struct S2Params {
   int h, w;              // array extent (input == intermediate == output)
   int shift_y, shift_x;  // source row / column of the first window cell for output (0,0)
+  int y0, y1;            // output rows produced
   int tiles_x, ntiles;
   int border, use_tma, zero_fill_ok, vec_store;
   unsigned long long fill_bits;
@@ -60,14 +61,14 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
   const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto tile_origin = [&](int i, int &oy0, int &ox0) {
     const int t = (int)blockIdx.x + i * (int)gridDim.x;
-    oy0 = (t / P.tiles_x) * C::TH;
+    oy0 = P.y0 + (t / P.tiles_x) * C::TH;
     ox0 = (t % P.tiles_x) * C::TW;
   };
   auto tma_ok = [&](int oy0, int ox0) -> bool {
     if (!TMA) return false;
     if (P.zero_fill_ok) return true;
     const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x;
-    const int th = min(C::TH, P.h - oy0), tw = min(C::TW, P.w - ox0);
+    const int th = min(C::TH, P.y1 - oy0), tw = min(C::TW, P.w - ox0);
     return by0 >= 0 && bx0 >= 0 && by0 + th + K - 1 <= P.h && bx0 + tw + K - 1 <= P.w;
   };
   auto issue = [&](int i) {
@@ -202,7 +203,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
         res[v] = acc;
       }
       const int gy = oy0 + ly + r, gx = ox0 + lx;
-      if (gy < P.h && gx < P.w) {
+      if (gy < P.y1 && gx < P.w) {
         T *dst = out + (size_t)gy * P.w + gx;
         if (P.vec_store && gx + V <= P.w) {
           uint4 u;
@@ -221,15 +222,18 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
 }
 
 template <typename T, bool REV, int K, int XOFF>
-static int launch_s2(Ctx *c, const Plan &p1, const Plan &p2, const void *d_in, void *d_out) {
+static int launch_s2(Ctx *c, const Plan &p1, const Plan &p2, const void *d_in, void *d_out, const OuterRange *range) {
   using C = S2Cfg<T, K, XOFF>;
   S2Params P;
   std::memset(&P, 0, sizeof(P));
   P.h = (int)p1.in_dims[0]; P.w = (int)p1.in_dims[1];
   P.shift_y = (int)(p2.shift[0] + p2.min_off[0]);
   P.shift_x = (int)(p1.shift[1] + p1.min_off[1]);
+  P.y0 = range ? (int)range->o0 : 0;
+  P.y1 = range ? (int)range->o1 : P.h;
+  if (P.y1 <= P.y0) return MB_OK;
   P.tiles_x = (P.w + C::TW - 1) / C::TW;
-  P.ntiles = P.tiles_x * ((P.h + C::TH - 1) / C::TH);
+  P.ntiles = P.tiles_x * ((P.y1 - P.y0 + C::TH - 1) / C::TH);
   P.border = p1.border;
   std::memcpy(&P.fill_bits, p1.fill, 8);
   bool fill_zero = p1.border == MB_FILL;
@@ -264,30 +268,30 @@ static int launch_s2(Ctx *c, const Plan &p1, const Plan &p2, const void *d_in, v
 }
 
 template <typename T, bool REV, int K>
-static int launch_s2_x(Ctx *c, const Plan &p1, const Plan &p2, const void *i, void *o) {
+static int launch_s2_x(Ctx *c, const Plan &p1, const Plan &p2, const void *i, void *o, const OuterRange *r) {
   constexpr int V = 16 / (int)sizeof(T);
   const int sx = (int)(p1.shift[1] + p1.min_off[1]);
   const int xoff = ((sx % V) + V) % V;
   constexpr int NAT = (V - ((K / 2) % V)) % V;
-  if (xoff == 0) return launch_s2<T, REV, K, 0>(c, p1, p2, i, o);
+  if (xoff == 0) return launch_s2<T, REV, K, 0>(c, p1, p2, i, o, r);
   if constexpr (NAT != 0) {
-    if (xoff == NAT) return launch_s2<T, REV, K, NAT>(c, p1, p2, i, o);
+    if (xoff == NAT) return launch_s2<T, REV, K, NAT>(c, p1, p2, i, o, r);
   }
   return -1;
 }
 
 template <typename T>
-static int launch_s2_t(Ctx *c, const Plan &p1, const Plan &p2, const void *i, void *o) {
+static int launch_s2_t(Ctx *c, const Plan &p1, const Plan &p2, const void *i, void *o, const OuterRange *r) {
   const bool rev = p1.kind == MB_CONV;
   const int k = (int)p1.size[1];
 #define MB_S2(KK)                                                                  \
-  if (k == KK) return rev ? launch_s2_x<T, true, KK>(c, p1, p2, i, o) : launch_s2_x<T, false, KK>(c, p1, p2, i, o);
+  if (k == KK) return rev ? launch_s2_x<T, true, KK>(c, p1, p2, i, o, r) : launch_s2_x<T, false, KK>(c, p1, p2, i, o, r);
   MB_S2(3) MB_S2(5) MB_S2(7)
 #undef MB_S2
   return -1;
 }
 
-int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const void *d_in, void *d_out) {
+int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const void *d_in, void *d_out, const OuterRange *range) {
   const Plan &p1 = first.p, &p2 = second.p;
   if (p1.rank != 2 || p2.rank != 2 || !p1.unit_stride() || !p2.unit_stride()) return -1;
   if ((p1.kind != MB_CONV && p1.kind != MB_CORR) || p2.kind != p1.kind) return -1;
@@ -297,8 +301,8 @@ int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const vo
   if (p1.out_elems < c->tile_min_elems) return -1;
   if (p1.shift[0] + p1.min_off[0] != 0 || p2.shift[1] + p2.min_off[1] != 0) return -1;
   switch (p1.elem) {
-    case MB_F32: return launch_s2_t<float>(c, p1, p2, d_in, d_out);
-    case MB_F64: return launch_s2_t<double>(c, p1, p2, d_in, d_out);
+    case MB_F32: return launch_s2_t<float>(c, p1, p2, d_in, d_out, range);
+    case MB_F64: return launch_s2_t<double>(c, p1, p2, d_in, d_out, range);
   }
   return -1;
 }

@@ -23,8 +23,6 @@ namespace mb {
 
 enum { SW_TW = 128, SW_TH = 32, SW_CX = 4, SW_RY = 4, SW_S = 3, SW_MAX_TAPS = 1024, SW_MAX_WIN = 16 };
 
-// internal program: the descriptor's (mb_xop) plus "post-map with a constant" steps for fused fmap
-enum { SW_X_POST = 32 };  // op = SW_X_POST + mb_post, operand = c
 
 struct SWProgram {
   int n_terms, n_prog;
@@ -56,110 +54,94 @@ template <typename T> struct SWAcc {
   using Acc = typename A::Acc;
 };
 
-// one term over the thread's 16 outputs
-template <typename T>
-__device__ __forceinline__ void sw_term(int kind, int nt, int avg_n, const int *__restrict__ s_off, const T *__restrict__ s_k,
-                                        const T *__restrict__ base, int pitch, bool canon, bool skip_zero, T (&out)[SW_RY][SW_CX]) {
+// one term over RP rows x 4 columns (32 apart) of the thread's outputs, starting at `base`
+template <typename T, bool canon, int RP>
+__device__ __forceinline__ void sw_term_rows(int kind, int nt, int avg_n, const int *__restrict__ s_off, const T *__restrict__ s_k,
+                                             const T *__restrict__ base, int pitch, bool skip_zero, T (&out)[RP][SW_CX]) {
   using A = Arith<T>;
   using Acc = typename A::Acc;
-  Acc acc[SW_RY][SW_CX];
+  Acc acc[RP][SW_CX];
   auto ld = [&](int off, int r, int c) -> T {
     T v = base[off + r * pitch + 32 * c];
     if (canon) v = (T)(v != T(0));  // Storable Bool peek: (/= 0)
     return v;
   };
+#define SW_EACH(BODY)                      \
+  _Pragma("unroll") for (int r = 0; r < RP; ++r) _Pragma("unroll") for (int c = 0; c < SW_CX; ++c) { BODY; }
   switch (kind) {
     case MB_ID:
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) out[r][c] = ld(s_off[0], r, c);
+      SW_EACH(out[r][c] = ld(s_off[0], r, c))
       return;
     case MB_SUM: case MB_AVG:
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(0);
+      SW_EACH(acc[r][c] = A::from_count(0))
 #pragma unroll 1
       for (int t = 0; t < nt; ++t) {
         const int off = s_off[t];
-#pragma unroll
-        for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(acc[r][c], A::load(ld(off, r, c)));
+        SW_EACH(acc[r][c] = A::add(acc[r][c], A::load(ld(off, r, c))))
       }
       if (kind == MB_AVG) {
         const Acc n = A::from_count(avg_n);
-#pragma unroll
-        for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::div(acc[r][c], n);
+        SW_EACH(acc[r][c] = A::div(acc[r][c], n))
       }
       break;
     case MB_PRODUCT:
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(1);
+      SW_EACH(acc[r][c] = A::from_count(1))
 #pragma unroll 1
       for (int t = 0; t < nt; ++t) {
         const int off = s_off[t];
-#pragma unroll
-        for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::mul(acc[r][c], A::load(ld(off, r, c)));
+        SW_EACH(acc[r][c] = A::mul(acc[r][c], A::load(ld(off, r, c))))
       }
       break;
     case MB_MAX: case MB_MIN: {
       const bool mx = kind == MB_MAX;
-      T m[SW_RY][SW_CX];
+      T m[RP][SW_CX];
       const T init = mx ? (canon ? T(0) : Bounds<T>::lo()) : (canon ? T(1) : Bounds<T>::hi());
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) m[r][c] = init;
+      SW_EACH(m[r][c] = init)
 #pragma unroll 1
       for (int t = 0; t < nt; ++t) {
         const int off = s_off[t];
-#pragma unroll
-        for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-          for (int c = 0; c < SW_CX; ++c) {
-            const T x = ld(off, r, c);
-            m[r][c] = mx ? (x > m[r][c] ? x : m[r][c]) : (x < m[r][c] ? x : m[r][c]);
-          }
+        SW_EACH(const T x = ld(off, r, c); m[r][c] = mx ? (x > m[r][c] ? x : m[r][c]) : (x < m[r][c] ? x : m[r][c]))
       }
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) out[r][c] = m[r][c];
+      SW_EACH(out[r][c] = m[r][c])
       return;
     }
     default:  // MB_CONV / MB_CORR / MB_TAPS: acc = src * k + acc in the listed order (Convolution.hs:52-55, 74-78, 115-119)
-#pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::from_count(0);
+      SW_EACH(acc[r][c] = A::from_count(0))
+      if (skip_zero) {
 #pragma unroll 1
-      for (int t = 0; t < nt; ++t) {
-        const Acc kv = A::load(s_k[t]);
-        if (skip_zero && A::is_zero(kv)) continue;
-        const int off = s_off[t];
-#pragma unroll
-        for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-          for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(A::mul(A::load(ld(off, r, c)), kv), acc[r][c]);
+        for (int t = 0; t < nt; ++t) {
+          const Acc kv = A::load(s_k[t]);
+          if (A::is_zero(kv)) continue;
+          const int off = s_off[t];
+          SW_EACH(acc[r][c] = A::add(A::mul(A::load(ld(off, r, c)), kv), acc[r][c]))
+        }
+      } else {
+        // two taps per trip: the second tap's table and data loads are in flight while the first is accumulated
+        int t = 0;
+#pragma unroll 1
+        for (; t + 2 <= nt; t += 2) {
+          const Acc k0 = A::load(s_k[t]), k1 = A::load(s_k[t + 1]);
+          const int o0 = s_off[t], o1 = s_off[t + 1];
+          T x0[RP][SW_CX], x1[RP][SW_CX];
+          SW_EACH(x0[r][c] = ld(o0, r, c))
+          SW_EACH(x1[r][c] = ld(o1, r, c))
+          SW_EACH(acc[r][c] = A::add(A::mul(A::load(x0[r][c]), k0), acc[r][c]))
+          SW_EACH(acc[r][c] = A::add(A::mul(A::load(x1[r][c]), k1), acc[r][c]))
+        }
+        if (t < nt) {
+          const Acc kv = A::load(s_k[t]);
+          const int off = s_off[t];
+          SW_EACH(acc[r][c] = A::add(A::mul(A::load(ld(off, r, c)), kv), acc[r][c]))
+        }
       }
       break;
   }
-#pragma unroll
-  for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-    for (int c = 0; c < SW_CX; ++c) out[r][c] = A::store(acc[r][c]);
+  SW_EACH(out[r][c] = A::store(acc[r][c]))
+#undef SW_EACH
 }
 
-template <typename T, bool TMA>
-__global__ void __launch_bounds__(256)
+template <typename T, bool TMA, bool CANON>
+__global__ void __launch_bounds__(256, 2)
 smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SWParams P, const T *__restrict__ in, T *__restrict__ out) {
   constexpr int V = 16 / (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -210,7 +192,7 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   }
   const int lane = tid & 31, warp = tid >> 5;
   uint32_t phase = 0;
-  const bool canon = P.bool_canon != 0, skip = P.skip_zero != 0;
+  const bool skip = P.skip_zero != 0;
 
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i % SW_S;
@@ -242,70 +224,67 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       __syncthreads();
     }
 
-    // ---- compute: 4 x 4 outputs per thread, columns 32 apart ----
+    // ---- compute: 4 x 4 outputs per thread (columns 32 apart), RP rows at a time ----
+    // The host has turned the postfix program (Stencil/Internal.hs:104-111) into steps on two fixed value slots
+    // (programs that need a deeper stack take the generic kernel): a term is evaluated where the program pushes it,
+    // every step updates its slot in place.  8-byte elements go two rows at a time to stay within 128 registers.
+    constexpr int RP = sizeof(T) == 8 ? 2 : 4;
     const T *base = sm + (warp * SW_RY) * pitch + lane;
-    T res[SW_RY][SW_CX];
-    if (P.trivial) {
-      sw_term<T>(P.X.term_kind[0], P.X.term_ntaps[0], P.X.term_avg_n[0], s_off, s_k, base, pitch, canon, skip, res);
-    } else {
-      // every term at the same index, then the postfix program over the 16 values at once (Stencil/Internal.hs:104-111)
-      T tv[MB_MAX_TERMS][SW_RY][SW_CX];
-      for (int t = 0; t < P.X.n_terms; ++t)
-        sw_term<T>(P.X.term_kind[t], P.X.term_ntaps[t], P.X.term_avg_n[t], s_off + P.X.term_begin[t], s_k + P.X.term_begin[t], base,
-                   pitch, canon, skip, tv[t]);
-      T stack[MB_MAX_STACK][SW_RY][SW_CX];
-      int sp = 0;
-      for (int k = 0; k < P.X.n_prog; ++k) {
-        const int op = P.X.op[k];
-        T cv;
-        {
-          unsigned long long b = P.X.operand[k];
-          memcpy(&cv, &b, sizeof(T));
-        }
-        if (op == MB_X_TERM) {
-          const int t = P.X.arg[k];
-#pragma unroll
-          for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-            for (int c = 0; c < SW_CX; ++c) stack[sp][r][c] = tv[t][r][c];
-          ++sp;
-        } else if (op == MB_X_CONST) {
-#pragma unroll
-          for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-            for (int c = 0; c < SW_CX; ++c) stack[sp][r][c] = cv;
-          ++sp;
-        } else if (op >= SW_X_POST) {
-#pragma unroll
-          for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = post_one<T>(op - SW_X_POST, stack[sp - 1][r][c], cv);
-        } else if (op <= MB_X_MAX) {
-          --sp;
-#pragma unroll
-          for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = xop_binary<T>(op, stack[sp - 1][r][c], stack[sp][r][c]);
-        } else {
-#pragma unroll
-          for (int r = 0; r < SW_RY; ++r)
-#pragma unroll
-            for (int c = 0; c < SW_CX; ++c) stack[sp - 1][r][c] = xop_unary<T>(op, stack[sp - 1][r][c]);
+#pragma unroll 1
+    for (int r0 = 0; r0 < SW_RY; r0 += RP) {
+      const T *rbase = base + r0 * pitch;
+      T va[RP][SW_CX], vb[RP][SW_CX];
+#define SW_EACH(BODY)                      \
+  _Pragma("unroll") for (int r = 0; r < RP; ++r) _Pragma("unroll") for (int c = 0; c < SW_CX; ++c) { BODY; }
+      if (P.trivial) {
+        sw_term_rows<T, CANON, RP>(P.X.term_kind[0], P.X.term_ntaps[0], P.X.term_avg_n[0], s_off, s_k, rbase, pitch, skip, va);
+      } else {
+        SW_EACH(va[r][c] = vb[r][c] = T(0))
+#pragma unroll 1
+        for (int k = 0; k < P.X.n_prog; ++k) {
+          const int code = P.X.op[k];
+          const int op = code & 31, form = (code >> 5) & 3;
+          const bool on_b = (code & 0x80) != 0;
+          T cv;
+          {
+            unsigned long long b = P.X.operand[k];
+            memcpy(&cv, &b, sizeof(T));
+          }
+          if (form == 1) {  // slot <- slot op c
+            if (on_b) { SW_EACH(vb[r][c] = xop_binary<T>(op, vb[r][c], cv)) } else { SW_EACH(va[r][c] = xop_binary<T>(op, va[r][c], cv)) }
+          } else if (form == 2) {  // slot <- c op slot
+            if (on_b) { SW_EACH(vb[r][c] = xop_binary<T>(op, cv, vb[r][c])) } else { SW_EACH(va[r][c] = xop_binary<T>(op, cv, va[r][c])) }
+          } else if (form == 3) {  // a <- b op a
+            SW_EACH(va[r][c] = xop_binary<T>(op, vb[r][c], va[r][c]))
+          } else if (op == MB_X_TERM) {
+            const int t = P.X.arg[k];
+            if (on_b)
+              sw_term_rows<T, CANON, RP>(P.X.term_kind[t], P.X.term_ntaps[t], P.X.term_avg_n[t], s_off + P.X.term_begin[t],
+                                         s_k + P.X.term_begin[t], rbase, pitch, skip, vb);
+            else
+              sw_term_rows<T, CANON, RP>(P.X.term_kind[t], P.X.term_ntaps[t], P.X.term_avg_n[t], s_off + P.X.term_begin[t],
+                                         s_k + P.X.term_begin[t], rbase, pitch, skip, va);
+          } else if (op == MB_X_CONST) {
+            if (on_b) { SW_EACH(vb[r][c] = cv) } else { SW_EACH(va[r][c] = cv) }
+          } else if (op <= MB_X_MAX) {  // a <- a op b
+            SW_EACH(va[r][c] = xop_binary<T>(op, va[r][c], vb[r][c]))
+          } else if (on_b) {
+            SW_EACH(vb[r][c] = xop_unary<T>(op, vb[r][c]))
+          } else {
+            SW_EACH(va[r][c] = xop_unary<T>(op, va[r][c]))
+          }
         }
       }
+#undef SW_EACH
 #pragma unroll
-      for (int r = 0; r < SW_RY; ++r)
+      for (int r = 0; r < RP; ++r) {
+        const int gy = oy0 + warp * SW_RY + r0 + r;
+        if (gy < P.y1) {
 #pragma unroll
-        for (int c = 0; c < SW_CX; ++c) res[r][c] = stack[0][r][c];
-    }
-#pragma unroll
-    for (int r = 0; r < SW_RY; ++r) {
-      const int gy = oy0 + warp * SW_RY + r;
-      if (gy < P.y1) {
-#pragma unroll
-        for (int c = 0; c < SW_CX; ++c) {
-          const int gx = ox0 + lane + 32 * c;
-          if (gx < P.out_w) out[(size_t)gy * P.out_w + gx] = res[r][c];
+          for (int c = 0; c < SW_CX; ++c) {
+            const int gx = ox0 + lane + 32 * c;
+            if (gx < P.out_w) out[(size_t)gy * P.out_w + gx] = va[r][c];
+          }
         }
       }
     }
@@ -314,15 +293,77 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   }
 }
 
-// the plan as (terms, program): single constructors become one term, MAG2 two terms and sqrt (a*a + b*b), post-maps
-// are appended as program steps — so that every fmap is applied in the store epilogue
+// The plan as terms + a program for the kernel's TWO value slots.  Single constructors are one term, MAG2 is
+// sqrt (a*a + b*b) of two, MB_EXPR brings its own postfix program, post-maps are further steps (so every fmap runs in
+// the store epilogue).  The postfix program is parsed into its tree and code is generated Sethi-Ullman style: a
+// subtree that is a chain of unary / with-constant operators over one term needs one slot; a binary node whose
+// operands both need two slots cannot be evaluated here (the generic kernel takes it).
+// step code: bit 7 = works on slot B; bits 5-6 = form (0 plain, 1 slot <- slot op c, 2 slot <- c op slot,
+// 3 a <- b op a); bits 0-4 = mb_xop.
+namespace {
+struct XNode {
+  int op = 0, arg = 0;
+  unsigned long long operand = 0;
+  int a = -1, b = -1;  // children
+};
+struct XGen {
+  std::vector<XNode> nodes;
+  SWProgram *X;
+  int n = 0;
+  bool ok = true;
+  void emit(int code, int arg, unsigned long long operand) {
+    if (n >= (int)sizeof(X->op)) { ok = false; return; }
+    X->op[n] = (unsigned char)code; X->arg[n] = (unsigned char)arg; X->operand[n] = operand;
+    ++n;
+  }
+  bool is_const(int i) const { return nodes[i].op == MB_X_CONST; }
+  bool is_binary(int i) const { return nodes[i].op >= MB_X_ADD && nodes[i].op <= MB_X_MAX; }
+  // can node i be evaluated in ONE slot?
+  bool single(int i) const {
+    const XNode &x = nodes[i];
+    if (x.op == MB_X_TERM || x.op == MB_X_CONST) return true;
+    if (is_binary(i)) return (is_const(x.b) && single(x.a)) || (is_const(x.a) && single(x.b));
+    return single(x.a);
+  }
+  void gen(int i, bool slot_b) {
+    if (!ok) return;
+    const XNode &x = nodes[i];
+    const int sb = slot_b ? 0x80 : 0;
+    if (x.op == MB_X_TERM || x.op == MB_X_CONST) { emit(x.op | sb, x.arg, x.operand); return; }
+    if (!is_binary(i)) { gen(x.a, slot_b); emit(x.op | sb, 0, 0); return; }
+    if (is_const(x.b)) { gen(x.a, slot_b); emit(x.op | (1 << 5) | sb, 0, nodes[x.b].operand); return; }
+    if (is_const(x.a)) { gen(x.b, slot_b); emit(x.op | (2 << 5) | sb, 0, nodes[x.a].operand); return; }
+    if (slot_b) { ok = false; return; }  // two live values and a third wanted
+    if (single(x.b)) { gen(x.a, false); gen(x.b, true); emit(x.op, 0, 0); return; }
+    if (single(x.a)) { gen(x.b, false); gen(x.a, true); emit(x.op | (3 << 5), 0, 0); return; }
+    ok = false;
+  }
+};
+}  // namespace
+
 static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coef) {
   std::memset(X, 0, sizeof(*X));
-  int n = 0;
-  auto push = [&](int op, int arg, const uint8_t *operand) {
-    X->op[n] = (unsigned char)op; X->arg[n] = (unsigned char)arg;
-    if (operand) std::memcpy(&X->operand[n], operand, 8);
-    ++n;
+  XGen g;
+  g.X = X;
+  std::vector<int> stack;
+  auto leaf = [&](int op, int arg, const uint8_t *operand) {
+    XNode nd;
+    nd.op = op; nd.arg = arg;
+    if (operand) std::memcpy(&nd.operand, operand, 8);
+    g.nodes.push_back(nd);
+    stack.push_back((int)g.nodes.size() - 1);
+  };
+  auto unary = [&](int op) {
+    XNode nd;
+    nd.op = op; nd.a = stack.back();
+    g.nodes.push_back(nd);
+    stack.back() = (int)g.nodes.size() - 1;
+  };
+  auto binary = [&](int op) {
+    XNode nd;
+    nd.op = op; nd.b = stack.back(); stack.pop_back(); nd.a = stack.back();
+    g.nodes.push_back(nd);
+    stack.back() = (int)g.nodes.size() - 1;
   };
   if (p.kind == MB_EXPR) {
     X->n_terms = (int)p.terms.size();
@@ -330,7 +371,11 @@ static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coe
       X->term_kind[t] = p.terms[t].kind; X->term_begin[t] = p.terms[t].begin;
       X->term_ntaps[t] = p.terms[t].ntaps; X->term_avg_n[t] = p.terms[t].avg_n;
     }
-    for (const mb_xins &x : p.prog) push(x.op, x.arg, x.operand);
+    for (const mb_xins &x : p.prog) {  // validated by the planner: no underflow, one value left
+      if (x.op == MB_X_TERM || x.op == MB_X_CONST) leaf(x.op, x.arg, x.operand);
+      else if (x.op <= MB_X_MAX) binary(x.op);
+      else unary(x.op);
+    }
     *coef = p.c1;
   } else if (p.kind == MB_MAG2) {
     const int nt = (int)p.ntaps;
@@ -342,8 +387,8 @@ static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coe
     coef->assign(p.c1.begin(), p.c1.end());
     coef->insert(coef->end(), p.c2.begin(), p.c2.end());
     // sqrt (fmap (^2) a + fmap (^2) b)  (Stencil/Internal.hs:105-146; Bench/Sobel.hs:39-44)
-    push(MB_X_TERM, 0, nullptr); push(MB_X_SQUARE, 0, nullptr); push(MB_X_TERM, 1, nullptr); push(MB_X_SQUARE, 0, nullptr);
-    push(MB_X_ADD, 0, nullptr); push(MB_X_SQRT, 0, nullptr);
+    leaf(MB_X_TERM, 0, nullptr); unary(MB_X_SQUARE); leaf(MB_X_TERM, 1, nullptr); unary(MB_X_SQUARE);
+    binary(MB_X_ADD); unary(MB_X_SQRT);
   } else {
     switch (p.kind) {
       case MB_ID: case MB_SUM: case MB_PRODUCT: case MB_AVG: case MB_MAX: case MB_MIN: case MB_CONV: case MB_CORR: case MB_TAPS: break;
@@ -351,15 +396,41 @@ static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coe
     }
     X->n_terms = 1;
     X->term_kind[0] = p.kind; X->term_begin[0] = 0; X->term_ntaps[0] = (int)p.ntaps; X->term_avg_n[0] = (int)p.avg_n;
-    push(MB_X_TERM, 0, nullptr);
+    leaf(MB_X_TERM, 0, nullptr);
     *coef = p.c1;
   }
-  for (const mb_post_op &q : p.post) push(SW_X_POST + q.op, 0, q.operand);
-  X->n_prog = n;
-  return true;
+  for (const mb_post_op &q : p.post) {  // fmap f: the same functions as operators with a constant
+    switch (q.op) {
+      case MB_POST_NEGATE: unary(MB_X_NEGATE); break;
+      case MB_POST_ABS: unary(MB_X_ABS); break;
+      case MB_POST_SIGNUM: unary(MB_X_SIGNUM); break;
+      case MB_POST_SQUARE: unary(MB_X_SQUARE); break;
+      case MB_POST_RECIP: unary(MB_X_RECIP); break;
+      case MB_POST_SQRT: unary(MB_X_SQRT); break;
+      case MB_POST_ADD: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_ADD); break;
+      case MB_POST_SUB: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_SUB); break;
+      case MB_POST_MUL: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_MUL); break;
+      case MB_POST_MIN: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_MIN); break;
+      case MB_POST_MAX: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_MAX); break;
+      case MB_POST_DIV: leaf(MB_X_CONST, 0, q.operand); binary(MB_X_DIV); break;
+      case MB_POST_RSUB: case MB_POST_RDIV: {  // c - x, c / x: the constant is the FIRST operand
+        const int x = stack.back();
+        stack.pop_back();
+        leaf(MB_X_CONST, 0, q.operand);
+        stack.push_back(x);
+        binary(q.op == MB_POST_RSUB ? MB_X_SUB : MB_X_DIV);
+        break;
+      }
+      default: return false;
+    }
+  }
+  if (stack.size() != 1) return false;
+  g.gen(stack.back(), false);
+  X->n_prog = g.n;
+  return g.ok;
 }
 
-template <typename T>
+template <typename T, bool CANON = false>
 static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void *d_coef, const void *d_taps2, const void *d_in, void *d_out,
                        const OuterRange *range) {
   constexpr int V = 16 / (int)sizeof(T);
@@ -398,8 +469,8 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   P.use_tma = (!c->no_tma && P.bw <= 256 && P.bh <= 256 && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box)) ? 1 : 0;
   const size_t smem_bytes = (size_t)SW_S * P.stage_bytes + 64 + (size_t)((P.ntaps + 3) & ~3) * 4 + (size_t)P.ntaps * sizeof(T) + 16;
   if (smem_bytes > 200 * 1024) return -1;
-  auto kern = P.use_tma ? smallwin_kernel<T, true> : smallwin_kernel<T, false>;
-  static bool configured[64][2] = {{false}};
+  auto kern = P.use_tma ? smallwin_kernel<T, true, CANON> : smallwin_kernel<T, false, CANON>;
+  static bool configured[64][2] = {{false}};  // (per instantiation: T, CANON)
   if (!configured[c->device & 63][P.use_tma]) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[c->device & 63][P.use_tma] = true;
@@ -452,7 +523,8 @@ int launch_smallwin(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
     case MB_U16: return launch_sw_t<uint16_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
     case MB_I16: return launch_sw_t<int16_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
     case MB_U32: return launch_sw_t<uint32_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
-    case MB_I32: case MB_BOOL32: return launch_sw_t<int32_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_I32: return launch_sw_t<int32_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
+    case MB_BOOL32: return launch_sw_t<int32_t, true>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
     case MB_U64: return launch_sw_t<uint64_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
     case MB_I64: return launch_sw_t<int64_t>(c, dp, X, d_coef, d_taps, d_in, d_out, range);
     case MB_F32: return launch_sw_t<float>(c, dp, X, d_coef, d_taps, d_in, d_out, range);

@@ -1,7 +1,10 @@
 // C-ABI entry points of libmassiv_b200.so (declared in include/massiv_b200.h): context, memory,
 // plan cache, kernel dispatch, run / iterate.  No torch types, no C++ exceptions across the boundary.
+#include <sched.h>
+
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <new>
 
 #include "mb_internal.h"
@@ -245,6 +248,44 @@ static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t
   return MB_OK;
 }
 
+// iterateUntil with a device-side predicate: chunks of check_every applications; the last application of a chunk is
+// a single step so that BOTH arrays the predicate compares exist (the fused two-step kernel never materialises the
+// state in between).
+static int iterate_until_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t *dims, void *a, void *b, int64_t max_steps,
+                                int64_t check_every, int predicate, double tol, int64_t *steps, int32_t *converged, void **result) {
+  if (max_steps < 1 || check_every < 1) return fail(c, MB_ERR_INVALID_DESC, "iterateUntil applies the step at least once");
+  if (predicate != MB_UNTIL_EQUAL && predicate != MB_UNTIL_MAX_ABS_DIFF) return fail(c, MB_ERR_INVALID_DESC, "unknown predicate");
+  if (predicate == MB_UNTIL_MAX_ABS_DIFF && desc->elem != MB_F32 && desc->elem != MB_F64)
+    return fail(c, MB_ERR_UNSUPPORTED, "the max-abs-difference predicate needs Float / Double elements");
+  std::shared_ptr<DevPlan> dp;
+  int st = get_dev_plan(c, desc, dims, &dp);
+  if (st) return st;
+  if (!dp->p.same_shape()) return fail(c, MB_ERR_SIZE_MISMATCH, "iterate needs output size == input size");
+  void *cur = a, *other = b;
+  int64_t done = 0;
+  *converged = 0;
+  while (done < max_steps) {
+    const int64_t chunk = std::min<int64_t>(check_every, max_steps - done);
+    if (chunk > 1) {
+      void *r = nullptr;
+      if ((st = iterate_dev_locked(c, desc, dims, cur, other, chunk - 1, &r))) return st;
+      if (r != cur) { other = cur; cur = r; }
+    }
+    if ((st = launch_plan(c, *dp, cur, other, nullptr))) return st;  // prev = cur, cur = other
+    void *prev = cur;
+    cur = other; other = prev;
+    done += chunk;
+    unsigned long long unequal = 0;
+    double maxd = 0.0;
+    if ((st = converge_check(c, desc->elem, cur, prev, (size_t)dp->p.out_elems, &unequal, &maxd))) return st;
+    const bool ok = predicate == MB_UNTIL_EQUAL ? unequal == 0 : maxd < tol;
+    if (ok) { *converged = 1; break; }
+  }
+  *steps = done;
+  *result = cur;
+  return MB_OK;
+}
+
 static int check_sep2(Ctx *c, const mb_stencil_desc *f, const mb_stencil_desc *s) {
   if (!f || !s) return fail(c, MB_ERR_INVALID_DESC, "null descriptor");
   if (f->elem != s->elem || f->rank != s->rank || f->border != s->border ||
@@ -253,7 +294,7 @@ static int check_sep2(Ctx *c, const mb_stencil_desc *f, const mb_stencil_desc *s
   return MB_OK;
 }
 
-int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const void *d_in, void *d_out);
+int run_sep2_fused(Ctx *c, const DevPlan &first, const DevPlan &second, const void *d_in, void *d_out, const OuterRange *range);
 
 static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_desc *s, const int64_t *dims,
                            const void *d_in, void *d_out, void *d_tmp) {
@@ -265,7 +306,7 @@ static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_de
   if (!p1->p.same_shape() || !p2->p.same_shape())
     return fail(c, MB_ERR_SIZE_MISMATCH, "separable passes must be mapStencil-shaped (same size in and out)");
   if (!c->force_generic && p1->p.post.empty() && p2->p.post.empty()) {
-    st = run_sep2_fused(c, *p1, *p2, d_in, d_out);
+    st = run_sep2_fused(c, *p1, *p2, d_in, d_out, nullptr);
     if (st != -1) return st;
   }
   if (!d_tmp) {
@@ -280,7 +321,9 @@ static int sep2_dev_locked(Ctx *c, const mb_stencil_desc *f, const mb_stencil_de
 // planes it reads (its own plus the stencil's reach) have landed, and leaves on a third stream while the
 // next chunk is computed.  PCIe is full duplex, so the two copies overlap each other as well as the
 // kernel.  -1: not worth it / not applicable (small arrays, strided evaluation): the caller runs serially.
-int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out, void *d_in, void *d_out) {
+// `launch` (optional): what produces output planes [o0, o1) from the device input; default: the plan itself
+int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out, void *d_in, void *d_out,
+                  const std::function<int(const OuterRange &)> *launch = nullptr) {
   const Plan &p = dp.p;
   if (!c->pipeline || !p.unit_stride() || p.out_elems == 0 || p.in_elems == 0) return -1;
   const size_t ib = (size_t)p.in_elems * p.esize, ob = (size_t)p.out_elems * p.esize;
@@ -342,7 +385,7 @@ int run_pipelined(Ctx *c, const DevPlan &dp, const void *host_in, void *host_out
       }
     }
     MB_PIPE(cudaStreamWaitEvent(c->stream, c->pipe_events[j_hi], 0));
-    int st = launch_plan(c, dp, d_in, d_out, &r);
+    int st = launch ? (*launch)(r) : launch_plan(c, dp, d_in, d_out, &r);
     if (st) return bail(st);
     MB_PIPE(cudaEventRecord(c->pipe_events[16 + k], c->stream));
     MB_PIPE(cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
@@ -449,6 +492,7 @@ int mb_ctx_destroy(mb_ctx *h) {
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->d_flag) cudaFree(c->d_flag);
+  if (c->d_conv) cudaFree(c->d_conv);
   for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
   if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -533,11 +577,64 @@ int mb_download(mb_ctx *h, void *dst, const void *src, size_t bytes) {
   return MB_OK;
 }
 
+// Pinned host memory is first touched (and therefore placed) by the thread that allocates it.  With eight ranks
+// copying 58 GB each at once, buffers on the wrong socket share the inter-socket link: the allocation therefore
+// runs with the thread bound to the CPUs of the device's NUMA node (sysfs), the old affinity is restored afterwards.
+// MASSIV_B200_NO_NUMA=1 switches it off; a machine without NUMA information (numa_node = -1) is left alone.
+static bool cpus_near_device(int device, cpu_set_t *set) {
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, (int)sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return false; }
+  for (char *q = bdf; *q; ++q) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+  char path[160];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+  FILE *f = std::fopen(path, "r");
+  if (!f) return false;
+  int node = -1;
+  const int got = std::fscanf(f, "%d", &node);
+  std::fclose(f);
+  if (got != 1 || node < 0) return false;
+  std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = std::fopen(path, "r");
+  if (!f) return false;
+  char list[1024] = {0};
+  const bool ok = std::fgets(list, sizeof(list), f) != nullptr;
+  std::fclose(f);
+  if (!ok) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (char *q = list; *q;) {  // "0-31,64-95"
+    char *e = nullptr;
+    long a = std::strtol(q, &e, 10);
+    if (e == q) break;
+    long b = a;
+    if (*e == '-') { q = e + 1; b = std::strtol(q, &e, 10); }
+    for (long v = a; v <= b && v < CPU_SETSIZE; ++v) { CPU_SET((int)v, set); ++n; }
+    q = (*e == ',') ? e + 1 : e;
+    if (*e != ',' ) break;
+  }
+  return n > 0;
+}
+
 int mb_host_alloc(mb_ctx *h, size_t bytes, void **p) {
   Guard g(h);
   if (g.st) return g.st;
   if (!p) return fail(g.c, MB_ERR_INVALID_DESC, "null out pointer");
-  MB_CUDA(g.c, cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+  cpu_set_t old_set, near_set;
+  bool bound = false;
+  if (!std::getenv("MASSIV_B200_NO_NUMA") && sched_getaffinity(0, sizeof(old_set), &old_set) == 0 &&
+      cpus_near_device(g.c->device, &near_set)) {
+    cpu_set_t both;
+    CPU_AND(&both, &old_set, &near_set);  // never leave the set the process was given
+    if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0) bound = true;
+  }
+  const cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e == cudaSuccess && bound && bytes) {
+    // first touch on this thread: one byte per page places the pages on the near node
+    volatile unsigned char *q = (volatile unsigned char *)*p;
+    for (size_t i = 0; i < bytes; i += 4096) q[i] = 0;
+  }
+  if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+  MB_CUDA(g.c, e);
   return MB_OK;
 }
 
@@ -597,6 +694,21 @@ int mb_run_sep2(mb_ctx *h, const mb_stencil_desc *f, const mb_stencil_desc *s, c
   void *d_in = nullptr, *d_out = nullptr;
   if ((st = ensure_scratch(c, 0, n ? n : 1, &d_in))) return st;
   if ((st = ensure_scratch(c, 1, n ? n : 1, &d_out))) return st;
+  {
+    // the fused kernel produces any range of output rows from the input rows it reads (the column pass's reach):
+    // the same three-stage pipeline as mb_run, driven by the second pass's geometry
+    std::shared_ptr<DevPlan> p1, p2;
+    if ((st = get_dev_plan(c, f, dims, &p1))) return st;
+    if ((st = get_dev_plan(c, s, dims, &p2))) return st;
+    if (p1->p.same_shape() && p2->p.same_shape() && !c->force_generic && p1->p.post.empty() && p2->p.post.empty()) {
+      // probe: does the fused kernel take these shapes?  (an empty range launches nothing)
+      const OuterRange none{0, 0};
+      if (run_sep2_fused(c, *p1, *p2, d_in, d_out, &none) == MB_OK) {
+        const std::function<int(const OuterRange &)> launch = [&](const OuterRange &r) { return run_sep2_fused(c, *p1, *p2, d_in, d_out, &r); };
+        if ((st = run_pipelined(c, *p2, host_in, host_out, d_in, d_out, &launch)) != -1) return st;
+      }
+    }
+  }
   if ((st = copy_h2d(c, d_in, host_in, n))) return st;
   if ((st = sep2_dev_locked(c, f, s, dims, d_in, d_out, nullptr))) return st;
   if ((st = copy_d2h(c, host_out, d_out, n))) return st;
@@ -626,6 +738,33 @@ int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, cons
   if ((st = ensure_scratch(c, 1, n ? n : 1, &b))) return st;
   if ((st = copy_h2d(c, a, host_in, n))) return st;
   if ((st = iterate_dev_locked(c, desc, dims, a, b, n_steps, &res))) return st;
+  if ((st = copy_d2h(c, host_out, res, n))) return st;
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+int mb_iterate_until_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, void *a, void *b, int64_t max_steps,
+                         int64_t check_every, int predicate, double tol, int64_t *steps, int32_t *converged, void **result) {
+  Guard g(h);
+  if (g.st) return g.st;
+  if (!desc || !dims || !steps || !converged || !result) return fail(g.c, MB_ERR_INVALID_DESC, "null argument");
+  return iterate_until_locked(g.c, desc, dims, a, b, max_steps, check_every, predicate, tol, steps, converged, result);
+}
+
+int mb_iterate_until(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in, void *host_out,
+                     int64_t max_steps, int64_t check_every, int predicate, double tol, int64_t *steps, int32_t *converged) {
+  Guard g(h);
+  if (g.st) return g.st;
+  Ctx *c = g.c;
+  if (!desc || !dims || !steps || !converged) return fail(c, MB_ERR_INVALID_DESC, "null argument");
+  size_t n = (size_t)mb_elem_size(desc->elem);
+  for (int i = 0; i < desc->rank; ++i) n *= (size_t)dims[i];
+  void *a = nullptr, *b = nullptr, *res = nullptr;
+  int st;
+  if ((st = ensure_scratch(c, 0, n ? n : 1, &a))) return st;
+  if ((st = ensure_scratch(c, 1, n ? n : 1, &b))) return st;
+  if ((st = copy_h2d(c, a, host_in, n))) return st;
+  if ((st = iterate_until_locked(c, desc, dims, a, b, max_steps, check_every, predicate, tol, steps, converged, &res))) return st;
   if ((st = copy_d2h(c, host_out, res, n))) return st;
   MB_CUDA(c, cudaStreamSynchronize(c->stream));
   return MB_OK;

@@ -103,6 +103,7 @@ struct Ctx {
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks
   unsigned *d_flag = nullptr;  // "the optimistic kernel met a non-finite value": set by it, read by the conditional redo
+  unsigned long long *d_conv = nullptr;  // convergence verdict of iterate_until (k_converge.cu)
   void *scratch[3] = {nullptr, nullptr, nullptr};
   size_t scratch_bytes[3] = {0, 0, 0};
   void *pinned = nullptr;
@@ -140,6 +141,8 @@ int launch_linescan(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
 int launch_direct2d(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range);  // -1: not applicable
 int launch_post(Ctx *c, const Plan &p, void *d_out, const OuterRange *range);  // in-place post-maps over the output
 int ensure_flag(Ctx *c);  // allocates c->d_flag
+// iterateUntil predicates: cells with !(cur == prev) and the largest |cur - prev| (blocks until known)
+int converge_check(Ctx *c, int elem, const void *cur, const void *prev, size_t n, unsigned long long *unequal, double *max_abs_diff);
 // strict 27-tap step that runs only when *cond != 0 (nullptr: always)
 int launch_vol3d_dense_cond(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const unsigned *cond);
 // dst <- src when *cond != 0

@@ -263,6 +263,8 @@ def _lift2(op: str, a, b) -> Stencil:
     if not isinstance(a, Stencil) or not isinstance(b, Stencil):
         return NotImplemented
     flags = (a.flags | b.flags) & _abi.FLAG_ASSUME_FINITE
+    if op == "mul" and a is b:   # s * s evaluates s twice in the reference; x * x is (^2) of one evaluation, bit for bit
+        return Stencil("expr", None, None, flags=flags, expr=_X("square", (_as_node(a),)))
     return Stencil("expr", None, None, flags=flags, expr=_X(op, (_as_node(a), _as_node(b))))
 
 
@@ -760,6 +762,38 @@ def iterateStencil(n: int, border: Border, stencil: Stencil, arr: Array, device:
     out = np.empty_like(dw.arr)
     dev.check(L.mb_iterate(dev.handle, C.byref(d), dims, C.c_void_p(dw.arr.ctypes.data), C.c_void_p(out.ctypes.data), n))
     return out
+
+
+def iterateUntil(predicate, border: Border, stencil: Stencil, arr: Array, max_steps: int, check_every: int = 1,
+                 device: Optional[Device] = None):
+    """``iterateUntil convergence (\\_ -> mapStencil border stencil) arr`` (Manifest/Internal.hs:331-349) with one of the
+    predicates the device can evaluate: ``"equal"`` (``\\_ prev cur -> cur == prev``) or ``("max_abs_diff", tol)``
+    (``maximum (abs (cur - prev)) < tol``), checked after every `check_every`-th application, at most `max_steps`
+    applications.  Returns (array, applications made, converged)."""
+    name, tol = (predicate, 0.0) if isinstance(predicate, str) else (predicate[0], float(predicate[1]))
+    pred = {"equal": _abi.UNTIL_EQUAL, "max_abs_diff": _abi.UNTIL_MAX_ABS_DIFF}[name]
+    dw = applyStencil(border, stencil._resolved(arr.ndim), arr) if isinstance(border, Padding) else mapStencil(border, stencil, arr)
+    dev = _device_of(dw, device)
+    d = dw.desc()
+    L = dev._L
+    dims = _abi.dims_array(dw.arr.shape)
+    steps, conv = C.c_int64(), C.c_int32()
+    if isinstance(arr, DeviceArray):
+        a = dev.alloc(arr.shape, arr.dtype, arr.elem)   # iterateUntil never mutates its argument
+        b = dev.alloc(arr.shape, arr.dtype, arr.elem)
+        if arr.nbytes:
+            idd = mapStencil(Edge, idStencil(arr.ndim), arr).desc()
+            dev.check(L.mb_run_dev(dev.handle, C.byref(idd), dims, C.c_void_p(arr.ptr), C.c_void_p(a.ptr)))
+        res = C.c_void_p()
+        dev.check(L.mb_iterate_until_dev(dev.handle, C.byref(d), dims, C.c_void_p(a.ptr), C.c_void_p(b.ptr), max_steps, check_every,
+                                         pred, tol, C.byref(steps), C.byref(conv), C.byref(res)))
+        keep, drop = (a, b) if res.value == a.ptr else (b, a)
+        drop.free()
+        return keep, steps.value, bool(conv.value)
+    out = np.empty_like(dw.arr)
+    dev.check(L.mb_iterate_until(dev.handle, C.byref(d), dims, C.c_void_p(dw.arr.ctypes.data), C.c_void_p(out.ctypes.data), max_steps,
+                                 check_every, pred, tol, C.byref(steps), C.byref(conv)))
+    return out, steps.value, bool(conv.value)
 
 
 def computeSeparable(border: Border, first: Stencil, second: Stencil, arr: Array, device: Optional[Device] = None) -> Array:

@@ -47,3 +47,23 @@ def test_other_shapes():
     post = M.avgStencil(M.Sz(3, 3)).fmap("mul", 2.0).fmap("abs")
     want = O.apply("avg", arr, size=(3, 3), border="edge", nthreads=16, post=[("mul", 2.0), ("abs",)])
     assert bits_equal(M.compute(M.mapStencil(M.Edge, post, arr)), want)
+
+
+@pytest.mark.parametrize("border", ["edge", "wrap", "fill"])
+def test_separable_two_pass_host_to_host(border):
+    """mb_run_sep2 pipelines the fused separable kernel over row chunks the same way; the result must be that of the two
+    computes (intermediate rounded to Float) whatever the chunking."""
+    dev = M.Device.default()
+    rng = np.random.default_rng(13)
+    img = rng.random((6200, 6100)).astype(np.float32)
+    g = np.array([0.05, 0.1, 0.2, 0.3, 0.2, 0.1, 0.05], np.float32)
+    row, col = M.makeConvolutionStencilFromKernel(g.reshape(1, 7)), M.makeConvolutionStencilFromKernel(g.reshape(7, 1))
+    t = O.apply("conv", img, size=(1, 7), coeffs=g.tolist(), border=border, fill=0.25, nthreads=16)
+    want = O.apply("conv", t, size=(7, 1), coeffs=g.tolist(), border=border, fill=0.25, nthreads=16)
+    got = M.computeSeparable(border_obj(border, 0.25), row, col, img)
+    assert dev.last_kernel == "sep2d" and bits_equal(got, want)
+    dev.set_option("pipeline", 0)
+    try:
+        assert bits_equal(M.computeSeparable(border_obj(border, 0.25), row, col, img), want)
+    finally:
+        dev.set_option("pipeline", 1)
