@@ -18,6 +18,9 @@
 //   applyStencil, mapStencil (Array/Stencil.hs:76-86,187-217)  same names -> DW<E>
 //   compute, computeWithStride (Array/Manifest/Internal.hs)    same names (take the Device)
 //   iterateUntil (\n _ _ -> n >= k-1) (\_ -> mapStencil b st) iterateStencil
+//   iterateUntil (\_ p c -> c == p | maximum |c - p| < tol)    iterateUntil (Until::Equal / Until::MaxAbsDiff)
+//   Applicative / Num / Fractional / Floating (Stencil ix e)   operators + - * / on two stencils, abs, signum,
+//     (Array/Stencil/Internal.hs:83-174)                         recip, sqrt, square, minStencils, maxStencils, pure
 //   midpoint/trapezoid/simpsonsStencil, integrateWith          same names (Array/Numeric/Integral.hs)
 //   IndexZeroException, SizeMismatchException                  same names
 #ifndef MASSIV_B200_HPP
@@ -96,11 +99,41 @@ template <typename E> struct Stencil {
   std::vector<int64_t> tap_offsets;  // TAPS: ntaps * rank, application order
   uint32_t flags = 0;
   std::vector<mb_post_op> post;
+  // kind MB_EXPR (liftA2 / fmap / pure over built-in stencils, Array/Stencil/Internal.hs:93-174): the sub-stencils
+  // and the postfix program; size / center hold the union of Internal.hs:83-90
+  std::vector<Stencil> terms;
+  std::vector<mb_xins> program;
 
   // Functor / Num / Fractional / Floating instances (Array/Stencil/Internal.hs:36-41, 114-146) for the
   // functions with an exactly specified result; everything else is a closure and stays on massiv's CPU path
   Stencil fmap(mb_post op, E c = E()) const {
     Stencil s = *this;
+    if (kind == MB_EXPR) {  // fmap over an expression: further program steps
+      mb_xins k;
+      std::memset(&k, 0, sizeof(k));
+      k.op = MB_X_CONST;
+      std::memcpy(k.operand, &c, sizeof(E));
+      mb_xins o;
+      std::memset(&o, 0, sizeof(o));
+      switch (op) {
+        case MB_POST_NEGATE: o.op = MB_X_NEGATE; break;
+        case MB_POST_ABS: o.op = MB_X_ABS; break;
+        case MB_POST_SIGNUM: o.op = MB_X_SIGNUM; break;
+        case MB_POST_SQUARE: o.op = MB_X_SQUARE; break;
+        case MB_POST_RECIP: o.op = MB_X_RECIP; break;
+        case MB_POST_SQRT: o.op = MB_X_SQRT; break;
+        case MB_POST_ADD: s.program.push_back(k); o.op = MB_X_ADD; break;
+        case MB_POST_SUB: s.program.push_back(k); o.op = MB_X_SUB; break;
+        case MB_POST_MUL: s.program.push_back(k); o.op = MB_X_MUL; break;
+        case MB_POST_MIN: s.program.push_back(k); o.op = MB_X_MIN; break;
+        case MB_POST_MAX: s.program.push_back(k); o.op = MB_X_MAX; break;
+        case MB_POST_DIV: s.program.push_back(k); o.op = MB_X_DIV; break;
+        case MB_POST_RSUB: s.program.insert(s.program.begin(), k); o.op = MB_X_SUB; break;
+        default: s.program.insert(s.program.begin(), k); o.op = MB_X_DIV; break;
+      }
+      s.program.push_back(o);
+      return s;
+    }
     mb_post_op p;
     std::memset(&p, 0, sizeof(p));
     p.op = op;
@@ -115,6 +148,76 @@ template <typename E> struct Stencil {
   Stencil operator/(E c) const { return fmap(MB_POST_DIV, c); }
   Stencil assumeFinite() const { Stencil s = *this; s.flags |= MB_FLAG_ASSUME_FINITE; return s; }
 };
+namespace detail {
+inline mb_xins xins(int op, int arg = 0) {
+  mb_xins x;
+  std::memset(&x, 0, sizeof(x));
+  x.op = op; x.arg = arg;
+  return x;
+}
+// a stencil as (terms, program): a built-in one is a single term; its post-maps become program steps
+template <typename E> void as_expr(const Stencil<E> &s, std::vector<Stencil<E>> *terms, std::vector<mb_xins> *prog) {
+  const int base = (int)terms->size();
+  std::vector<mb_xins> body;
+  if (s.kind == MB_EXPR) {
+    for (const Stencil<E> &t : s.terms) terms->push_back(t);
+    for (mb_xins x : s.program) { if (x.op == MB_X_TERM) x.arg += base; body.push_back(x); }
+  } else {
+    if (s.kind == MB_LIFE || s.kind == MB_MAG2 || s.kind >= MB_INT_MIDPOINT) throw B200Error(MB_ERR_UNSUPPORTED, "this stencil does not combine into expressions");
+    Stencil<E> t = s;
+    t.post.clear(); t.flags = 0;
+    terms->push_back(t);
+    body.push_back(xins(MB_X_TERM, base));
+  }
+  for (const mb_post_op &q : s.post) {
+    mb_xins c = xins(MB_X_CONST);
+    std::memcpy(c.operand, q.operand, 8);
+    switch (q.op) {
+      case MB_POST_NEGATE: body.push_back(xins(MB_X_NEGATE)); break;
+      case MB_POST_ABS: body.push_back(xins(MB_X_ABS)); break;
+      case MB_POST_SIGNUM: body.push_back(xins(MB_X_SIGNUM)); break;
+      case MB_POST_SQUARE: body.push_back(xins(MB_X_SQUARE)); break;
+      case MB_POST_RECIP: body.push_back(xins(MB_X_RECIP)); break;
+      case MB_POST_SQRT: body.push_back(xins(MB_X_SQRT)); break;
+      case MB_POST_ADD: body.push_back(c); body.push_back(xins(MB_X_ADD)); break;
+      case MB_POST_SUB: body.push_back(c); body.push_back(xins(MB_X_SUB)); break;
+      case MB_POST_MUL: body.push_back(c); body.push_back(xins(MB_X_MUL)); break;
+      case MB_POST_MIN: body.push_back(c); body.push_back(xins(MB_X_MIN)); break;
+      case MB_POST_MAX: body.push_back(c); body.push_back(xins(MB_X_MAX)); break;
+      case MB_POST_DIV: body.push_back(c); body.push_back(xins(MB_X_DIV)); break;
+      case MB_POST_RSUB: body.insert(body.begin(), c); body.push_back(xins(MB_X_SUB)); break;  // c - x
+      default: body.insert(body.begin(), c); body.push_back(xins(MB_X_DIV)); break;             // MB_POST_RDIV: c / x
+    }
+  }
+  prog->insert(prog->end(), body.begin(), body.end());
+}
+template <typename E> int64_t geom_of(const Stencil<E> &s, size_t i) { return (s.kind == MB_AVG && s.size[i] < 1) ? 1 : s.size[i]; }
+// liftA2 f a b: both evaluated at the same index; centre = max of the centres, size = centre + max (size - centre)
+template <typename E> Stencil<E> lift2(int op, const Stencil<E> &a, const Stencil<E> &b) {
+  if (a.size.size() != b.size.size()) throw B200Error(MB_ERR_INVALID_DESC, "stencils of different ranks");
+  Stencil<E> r;
+  r.kind = MB_EXPR;
+  r.flags = (a.flags | b.flags) & MB_FLAG_ASSUME_FINITE;
+  as_expr(a, &r.terms, &r.program);
+  as_expr(b, &r.terms, &r.program);
+  r.program.push_back(xins(op));
+  for (size_t i = 0; i < a.size.size(); ++i) {
+    const int64_t c = a.center[i] > b.center[i] ? a.center[i] : b.center[i];
+    const int64_t ea = geom_of(a, i) - a.center[i], eb = geom_of(b, i) - b.center[i];
+    r.center.push_back(c);
+    r.size.push_back(c + (ea > eb ? ea : eb));
+  }
+  return r;
+}
+}  // namespace detail
+// Num / Fractional instances on two stencils (Array/Stencil/Internal.hs:114-131): liftA2 (+), (-), (*), (/)
+template <typename E> Stencil<E> operator+(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_ADD, a, b); }
+template <typename E> Stencil<E> operator-(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_SUB, a, b); }
+template <typename E> Stencil<E> operator*(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_MUL, a, b); }
+template <typename E> Stencil<E> operator/(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_DIV, a, b); }
+template <typename E> Stencil<E> minStencils(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_MIN, a, b); }  // liftA2 min
+template <typename E> Stencil<E> maxStencils(const Stencil<E> &a, const Stencil<E> &b) { return detail::lift2(MB_X_MAX, a, b); }  // liftA2 max
+template <typename E> Stencil<E> square(const Stencil<E> &s) { return s.fmap(MB_POST_SQUARE); }  // fmap (^2)
 template <typename E> Stencil<E> abs(const Stencil<E> &s) { return s.fmap(MB_POST_ABS); }
 template <typename E> Stencil<E> signum(const Stencil<E> &s) { return s.fmap(MB_POST_SIGNUM); }
 template <typename E> Stencil<E> recip(const Stencil<E> &s) { return s.fmap(MB_POST_RECIP); }
@@ -229,6 +332,7 @@ template <typename E> struct DW {
   Padding<E> padding;
   Stencil<E> stencil;
   const Array<E> *arr;
+  mutable std::vector<mb_term> term_store;  // MB_EXPR: the mb_term array the descriptor points at
   // fills a descriptor; the vectors referenced live in this object
   void describe(mb_stencil_desc *d, const Ix *stride) const {
     std::memset(d, 0, sizeof(*d));
@@ -251,6 +355,22 @@ template <typename E> struct DW {
     d->flags = stencil.flags;
     d->n_post = (uint32_t)stencil.post.size();
     d->post = stencil.post.empty() ? nullptr : stencil.post.data();
+    if (stencil.kind == MB_EXPR) {
+      term_store.assign(stencil.terms.size(), mb_term());
+      for (size_t t = 0; t < stencil.terms.size(); ++t) {
+        const Stencil<E> &ts = stencil.terms[t];
+        mb_term &m = term_store[t];
+        std::memset(&m, 0, sizeof(m));
+        m.kind = ts.kind;
+        for (int i = 0; i < rank; ++i) { m.size[i] = ts.size[(size_t)i]; m.center[i] = ts.center[(size_t)i]; }
+        m.coeffs = ts.coeffs.empty() ? nullptr : ts.coeffs.data();
+        if (ts.kind == MB_TAPS) { m.ntaps = (int64_t)ts.coeffs.size(); m.tap_offsets = ts.tap_offsets.data(); }
+      }
+      d->n_terms = (uint32_t)term_store.size();
+      d->terms = term_store.data();
+      d->n_program = (uint32_t)stencil.program.size();
+      d->program = stencil.program.data();
+    }
   }
 };
 template <typename E> DW<E> applyStencil(const Padding<E> &p, const Stencil<E> &st, const Array<E> &arr) { return {p, st, &arr}; }
@@ -320,6 +440,33 @@ template <typename E> Array<E> iterateStencil(const Device &dev, int64_t k, cons
   Array<E> out(arr.sz);
   dev.check(mb_iterate(dev.handle(), &d, arr.sz.dims.data(), arr.elems.data(), out.elems.data(), k));
   return out;
+}
+// iterateUntil convergence (\_ -> mapStencil border stencil) arr with a predicate the device can evaluate
+// (Array/Manifest/Internal.hs:331-349): Equal = \_ prev cur -> cur == prev; MaxAbsDiff tol = maximum |cur - prev| < tol;
+// checked after every checkEvery-th application, at most maxSteps applications
+struct Until {
+  mb_until predicate;
+  double tol;
+  static Until Equal() { return {MB_UNTIL_EQUAL, 0.0}; }
+  static Until MaxAbsDiff(double t) { return {MB_UNTIL_MAX_ABS_DIFF, t}; }
+};
+template <typename E> struct UntilResult {
+  Array<E> array;
+  int64_t steps;
+  bool converged;
+};
+template <typename E>
+UntilResult<E> iterateUntil(const Device &dev, const Until &u, int64_t maxSteps, int64_t checkEvery, const Border<E> &b, const Stencil<E> &st,
+                            const Array<E> &arr) {
+  const DW<E> dw = mapStencil(b, st, arr);
+  mb_stencil_desc d;
+  dw.describe(&d, nullptr);
+  UntilResult<E> r{Array<E>(arr.sz), 0, false};
+  int32_t conv = 0;
+  dev.check(mb_iterate_until(dev.handle(), &d, arr.sz.dims.data(), arr.elems.data(), r.array.elems.data(), maxSteps, checkEvery, u.predicate,
+                             u.tol, &r.steps, &conv));
+  r.converged = conv != 0;
+  return r;
 }
 // integrateWith (Array/Numeric/Integral.hs:121-135): computeWithStride (Stride nsz) $ mapStencil (Fill 0) (stencil dim n) arr
 template <typename E, typename F> Array<E> integrateWith(const Device &dev, F stencil, int dim, int n, const Array<E> &arr) {

@@ -140,11 +140,16 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     }
 
     // ---- pass 1: 1 x K along the rows of the box, result rounded to T into tbuf ----
-#pragma unroll 1
-    for (int rr = warp; rr < C::BH; rr += C::TY) {
+    // (fully unrolled: the trip count is fixed, the row's shared-memory address becomes an immediate offset; the
+    // Fill test only exists for tiles that touch the array's first or last rows)
+    const bool fill_rows = P.border == MB_FILL && (by0 < 0 || by0 + C::BH > P.h);
+#pragma unroll
+    for (int j = 0; j < (C::BH + C::TY - 1) / C::TY; ++j) {
+      const int rr = warp + j * C::TY;
+      if (rr >= C::BH) break;
       T res[V];
       const int gy = by0 + rr;
-      if (P.border == MB_FILL && (gy < 0 || gy >= P.h)) {
+      if (fill_rows && (gy < 0 || gy >= P.h)) {
         // the intermediate array is padded with the Fill element itself, not with a filtered fill row
 #pragma unroll
         for (int v = 0; v < V; ++v) res[v] = fillv;

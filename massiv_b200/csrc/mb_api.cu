@@ -165,6 +165,14 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
   if (!c->force_generic) {
     int st = range ? -1 : launch_life(c, dp, d_in, d_out);  // the Life kernels produce whole arrays
     if (st != -1) return st;
+    // Mapped stencils (fmap f) of small windows: the small-window kernel applies the maps in its store epilogue;
+    // behind the compile-time-shaped kernels they are a second pass over the output.  Measured (scripts/probe_post.py,
+    // 16384^2): conv 3x3 |.|*c Float 384 vs 218 Gcells/s, avg 3x3 + c Double 218 vs 123, conv 5x5 sqrt|.| Float 206 vs 181;
+    // without maps the shaped kernels win (563 vs 538, 605 vs 504, 396 vs 259).
+    if (c->prefer_smallwin || (!dp.p.post.empty() && dp.p.ntaps <= 32)) {
+      st = launch_smallwin(c, dp, d_in, d_out, range);
+      if (st != -1) return st;
+    }
     st = launch_tile2d(c, dp, d_in, d_out, range);
     if (st != -1) return st;
     st = launch_vol3d(c, dp, d_in, d_out, range);
@@ -525,6 +533,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "no_known") g.c->no_known = (int)value;
   else if (k == "tb2") g.c->tb2 = (int)value;
   else if (k == "no_p2p") g.c->no_p2p = (int)value;
+  else if (k == "prefer_smallwin") g.c->prefer_smallwin = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }

@@ -99,6 +99,7 @@ struct Ctx {
   int64_t tile_min_elems = 16384;  // below this many output cells the generic kernel is used
   int no_optimistic = 0;           // 1: never skip zero taps without the caller's promise (always the 27-tap kernel)
   int pipeline = 1;                // mb_run overlaps H2D / kernel / D2H over chunks of the outer dimension
+  int prefer_smallwin = 0;         // 1: rank-2 plans try the small-window kernel before the compile-time-shaped ones (measurements)
   int no_p2p = 0;                  // sharded iteration: halo planes by ncclSend/ncclRecv instead of peer-memory copies
   std::map<std::string, std::shared_ptr<DevPlan>> plans;  // keyed by descriptor + dims bytes
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks

@@ -50,6 +50,15 @@ static int geometry() {
   const auto p = samePadding(s, Border<int64_t>::Edge());
   CHECK((p.paddingFromOrigin == Ix{2, 1} && p.paddingFromBottom == Ix{0, 1}), "samePadding");
   CHECK((Sz{-3, 2}.dims == Ix{0, 2}), "Sz clamps negative extents");
+  {  // Stencil/Internal.hs:83-90: liftA2 unions centres and sizes: sum (Sz 3) [centre 0] + corr [1,2,3] [centre 1]
+    const Array<int64_t> k(Sz{3}, {1, 2, 3}), ys = iota<int64_t>(Sz{5}, 1);
+    const auto e = sumStencil<int64_t>(Sz{3}) + makeCorrelationStencilFromKernel(k);
+    CHECK((e.kind == MB_EXPR && e.center == Ix{1} && e.size == Ix{4} && e.terms.size() == 2 && e.program.size() == 3), "union of centres and sizes");
+    CHECK((outputSize(mapStencil(Border<int64_t>::Fill(0), e, ys)) == Sz{5}), "mapStencil of an expression keeps the size");
+    bool threw = false;  // (/) needs Fractional
+    try { outputSize(mapStencil(Border<int64_t>::Fill(0), e / e, ys)); } catch (const B200Error &x) { threw = x.status == MB_ERR_UNSUPPORTED; }
+    CHECK(threw, "(/) on Int stencils is rejected");
+  }
   return failures;
 }
 
@@ -157,6 +166,40 @@ static int gpu() {
       ok = std::memcmp(&w, &mapped.elems[i], 8) == 0;
     }
     CHECK(ok, "fmap abs, (* 2)");
+  }
+  {  // Num (Stencil ix e) on two stencils (Stencil/Internal.hs:104-131), hand-derived: over [1..5] under Fill 0
+     // sumStencil (Sz 3) gives [6,9,12,9,5], the correlation with [1,2,3] gives [8,14,20,26,14] (StencilSpec.hs:206)
+    const Array<int64_t> k(Sz{3}, {1, 2, 3}), ys = iota<int64_t>(Sz{5}, 1);
+    const auto s1 = sumStencil<int64_t>(Sz{3});
+    const auto s2 = makeCorrelationStencilFromKernel(k);
+    const auto b = Border<int64_t>::Fill(0);
+    CHECK((compute(dev, mapStencil(b, s1 + s2, ys)).elems == std::vector<int64_t>{14, 23, 32, 35, 19}), "s1 + s2");
+    CHECK((compute(dev, mapStencil(b, s1 * s2, ys)).elems == std::vector<int64_t>{48, 126, 240, 234, 70}), "s1 * s2");
+    CHECK((compute(dev, mapStencil(b, abs(s1 - s2), ys)).elems == std::vector<int64_t>{2, 5, 8, 17, 9}), "abs (s1 - s2)");
+    CHECK((compute(dev, mapStencil(b, maxStencils(s1, s2) - minStencils(s1, s2), ys)).elems == std::vector<int64_t>{2, 5, 8, 17, 9}), "liftA2 max - liftA2 min");
+    CHECK((compute(dev, mapStencil(b, (s1 + s2) * int64_t(2) - int64_t(1), ys)).elems == std::vector<int64_t>{27, 45, 63, 69, 37}), "fmap over an expression");
+  }
+  {  // the closure-form Sobel operator of the reference's benchmark (massiv-bench/src/Data/Massiv/Bench/Sobel.hs:15-44)
+     // against the same operator assembled from the FromKernel magnitude: equal wherever both are exact (Int-valued data)
+    const std::vector<std::pair<Ix, double>> sx = {{{-1, -1}, -1}, {{0, -1}, -2}, {{1, -1}, -1}, {{-1, 1}, 1}, {{0, 1}, 2}, {{1, 1}, 1}};
+    const std::vector<std::pair<Ix, double>> sy = {{{-1, -1}, -1}, {{-1, 0}, -2}, {{-1, 1}, -1}, {{1, -1}, 1}, {{1, 0}, 2}, {{1, 1}, 1}};
+    const auto cx = makeConvolutionStencil<double>(Sz{3, 3}, Ix{1, 1}, sx), cy = makeConvolutionStencil<double>(Sz{3, 3}, Ix{1, 1}, sy);
+    const auto op = sqrt(cx * cx + cy * cy);
+    Array<double> img(Sz{120, 200});
+    for (size_t i = 0; i < img.elems.size(); ++i) img.elems[i] = (double)((i * 2654435761u) % 256);
+    const Array<double> kx(Sz{3, 3}, {-1, 0, 1, -2, 0, 2, -1, 0, 1}), ky(Sz{3, 3}, {-1, -2, -1, 0, 0, 0, 1, 2, 1});
+    const auto ref = compute(dev, mapStencil(Border<double>::Edge(), magnitude(makeConvolutionStencilFromKernel(kx), makeConvolutionStencilFromKernel(ky)), img));
+    const auto got = compute(dev, mapStencil(Border<double>::Edge(), op, img));
+    CHECK((got == ref), "closure-form Sobel operator == kernel-form magnitude on integer-valued data");
+  }
+  {  // iterateUntil (\_ prev cur -> cur == prev): a block is a still life, found after one generation
+    Array<uint8_t> g(Sz{32, 64});
+    g.elems[5 * 64 + 5] = g.elems[5 * 64 + 6] = g.elems[6 * 64 + 5] = g.elems[6 * 64 + 6] = 1;
+    const auto r = iterateUntil(dev, Until::Equal(), 50, 1, Border<uint8_t>::Wrap(), lifeStencil(), g);
+    CHECK((r.converged && r.steps == 1 && r.array == g), "iterateUntil: fixed point of Life");
+    g.elems[20 * 64 + 30] = g.elems[20 * 64 + 31] = g.elems[20 * 64 + 32] = 1;  // plus a blinker: never equal
+    const auto q = iterateUntil(dev, Until::Equal(), 7, 1, Border<uint8_t>::Wrap(), lifeStencil(), g);
+    CHECK((!q.converged && q.steps == 7), "iterateUntil: the step cap ends an oscillator");
   }
   {  // exceptions: IndexZeroException, SizeMismatchException
     bool threw = false;

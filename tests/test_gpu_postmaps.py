@@ -72,6 +72,8 @@ def test_behind_every_family(dev):
         ("conv", rng.standard_normal((70, 90)), dict(size=(3, 3), coeffs=k3.reshape(-1).tolist(), border="reflect"), M.makeConvolutionStencilFromKernel(k3), None),
         ("conv", rng.standard_normal((70, 90)), dict(size=(3, 3), coeffs=sob.reshape(-1).tolist(), border="edge"), M.makeConvolutionStencilFromKernel(sob), None),
         ("avg", rng.standard_normal((64, 80)), dict(size=(3, 3), border="edge"), M.avgStencil(M.Sz(3, 3)), None),
+        # 49 taps: the compile-time-shaped kernel + the post-map pass (small windows take the fused small-window kernel)
+        ("sum", rng.standard_normal((70, 90)), dict(size=(7, 7), border="reflect"), M.sumStencil(M.Sz(7, 7)), None),
         ("conv", rng.standard_normal((20, 36, 40)), dict(size=(3, 3, 3), coeffs=k333.reshape(-1).tolist(), border="fill", fill=0.0), M.makeConvolutionStencilFromKernel(k333).assumeFinite(), None),
         ("conv", rng.standard_normal((20, 36, 40)), dict(size=(3, 3, 3), coeffs=rng.standard_normal(27).tolist(), border="wrap"), None, None),
         ("sum", rng.standard_normal((40, 640)), dict(size=(1, 16), border="fill", fill=0.0, stride=(1, 16)), M.Stencil("sum", (1, 16)), (1, 16)),
@@ -87,7 +89,7 @@ def test_behind_every_family(dev):
         got = M.computeWithStride(stride, M.mapStencil(b, chain(st), dev.fromHost(arr))).toHost()
         seen.add(dev.last_kernel)
         assert bits_equal(got, want), (kind, kw["size"], dev.last_kernel)
-    assert {"tile2d", "tile2d_known", "vol3d_star7", "vol3d_dense27", "linescan_rows", "linescan_cols", "direct2d", "generic"} <= seen, seen
+    assert {"tile2d", "smallwin", "vol3d_star7", "vol3d_dense27", "linescan_rows", "linescan_cols", "direct2d", "generic"} <= seen, seen
 
 
 def test_iterate_and_separable(dev):
