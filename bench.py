@@ -25,6 +25,7 @@ Workloads (BASELINE.json configs):
     pool3 / simpson   SURVEY §8 (f) rows: strided evaluation
     sobel_operator / sobel_closure   the reference's published Sobel benchmark (closure-form stencils) at its own size and large
     sum9x9_u8   a 9x9 window over a Word8 image (small-window kernel)
+    avg3d       avgStencil 3x3x3 Float 1024^3 (small-window kernel, rank 3)
 
 `--impl reference` times the CPU restatement of massiv's Par path (oracle/, a pinned number of host threads) on a
 bounded sample of the same workload: no GHC exists in this image, so massiv itself cannot run.
@@ -71,6 +72,8 @@ WORKLOADS = {
                           text="Sobel operator, closure form (makeConvolutionStencil x2, sqrt (sX*sX + sY*sY)), Double 16384^2, Edge"),
     "sum9x9_u8": dict(dtype="u8", grid=(32768, 32768), bpc=2, iterated=False, config_id="a17", u8_full=True,
                       text="sumStencil (Sz2 9 9) Word8 (mod 256), Edge, 32768^2: a 9x9 window on a byte image"),
+    "avg3d": dict(dtype="f32", grid=(1024, 1024, 1024), bpc=8, iterated=False, config_id="a8",
+                  text="avgStencil (Sz3 3 3 3) Float, Edge, 1024^3: a 3-D fold (small-window kernel, rank 3)"),
     "simpson": dict(dtype="f64", grid=(16384, 16385), stride=(1, 16), iterated=False, config_id="f2",
                     text="integrateWith simpsonsStencil (Dim 1) 16: Simpson's rule along the rows, Double, Fill 0 "
                          "(Numeric/Integral.hs:99-135)"),
@@ -82,7 +85,7 @@ SIMPSON_DX = 1.0 / 16.0
 # enough for the clock sampler to see it)
 CONFIG_RUNS = [("life", 1000), ("avg3x3", 200), ("sobel", 100), ("gauss7", 50), ("gauss7sep", 100),
                # beyond BASELINE.json's list: the reference's published benchmark and the small-window kernel's proofs
-               ("sobel_operator", 2000), ("sobel_closure", 50), ("sum9x9_u8", 20)]
+               ("sobel_operator", 2000), ("sobel_closure", 50), ("sum9x9_u8", 20), ("avg3d", 20)]
 # measured unfused FP32 rate (mul and add issued separately, scripts/micro/fp_rate.cu on this pool's B200)
 FP32_OPS_PER_S = 35.0e12
 REF_THREADS = 16  # the reference arm and cpu_baseline use min(this, host cores) threads so that ratios compare across boxes
@@ -156,7 +159,7 @@ def oracle_from_desc(O, dw, a, threads, stride=None):
 
 def oracle_pass(O, name, a, threads):
     """one pass of the workload through the CPU oracle (gauss7sep: massiv's two computes, intermediate rounded)"""
-    if name in ("sobel_operator", "sobel_closure", "sum9x9_u8"):
+    if name in ("sobel_operator", "sobel_closure", "sum9x9_u8", "avg3d"):
         import massiv_b200 as M   # host-side lowering only (numpy in, descriptor out): no device involved
         spec = stencil_spec(name, M)
         return oracle_from_desc(O, M.mapStencil(spec[0], spec[1], a), a, threads)
@@ -197,6 +200,8 @@ def stencil_spec(name, M):
         return M.Edge, M.sqrt(sx * sx + sy * sy)   # Bench/Sobel.hs:39-44
     if name == "sum9x9_u8":
         return M.Edge, M.sumStencil(M.Sz(9, 9))
+    if name == "avg3d":
+        return M.Edge, M.avgStencil(M.Sz(3, 3, 3))
     if name == "simpson":
         from massiv_b200 import integral as I
         return M.Fill(0.0), I.simpsonsStencil(np.float64(SIMPSON_DX), 1, 16)
@@ -345,7 +350,7 @@ def cpu_sample_shape(name):
         return (48, g[1], g[2]), 2
     if name == "life":
         return g, 20
-    return (min(4096, g[0]), g[1]), 1
+    return ((min(4096, g[0]), g[1]) if len(g) == 2 else (48,) + tuple(g[1:])), 1
 
 
 def run_cpu(name, steps, warmup, threads=None):
@@ -666,7 +671,7 @@ def verify_life(env, grid, gens=64):
             "ok": bool(mism == 0 and eq and k1 == "life_bits")}
 
 
-def verify_single_pass(env, name, bufs, run, rows=4096):
+def verify_single_pass(env, name, bufs, run, rows=None):
     """Full size: the dispatched kernel against the library's generic kernel (an independent code path) bit for bit
     on the device; a random `rows`-row sub-slab of the output (with the stencil's reach of input rows either side)
     against the CPU oracle."""
@@ -674,6 +679,7 @@ def verify_single_pass(env, name, bufs, run, rows=4096):
     from oracle import oracle as O
     a_t, b_t = bufs
     grid = tuple(a_t.shape)
+    rows = rows or (4096 if len(grid) == 2 else 48)
     run(1)
     torch.cuda.synchronize()
     k1 = dev.last_kernel

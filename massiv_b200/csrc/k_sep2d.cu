@@ -36,7 +36,13 @@ template <typename T, int K, int XOFF> struct S2Cfg {
   static constexpr int BW = TW + HALO, BH = TH + K - 1;
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
   static constexpr int TBUF = ((TW * BH * (int)sizeof(T) + 127) / 128) * 128;
-  static constexpr int S = 3;
+// ring depth: two stages make three CTAs fit an SM (62 KB each) instead of two — 24 warps hide the barrier and
+// shared-memory waits between the two passes far better than a third tile in flight does:
+// Gauss 7x7 Float 32768^2: S = 2: 593-597 Gcells/s, S = 3: 490-498, S = 4: 499 (same box)
+#ifndef MB_S2_S
+#define MB_S2_S 2
+#endif
+  static constexpr int S = MB_S2_S;
   static constexpr int SMEM = S * STAGE + TBUF + 64;
 };
 

@@ -14,6 +14,8 @@
 // size, window offset or alignment.  The bound is the shared-memory pipe: one LDS per tap and output,
 // 32 lanes per clock and SM.  Tap order and the one-rounding-per-operation arithmetic are the reference's
 // (mb_arith.cuh), so results are bit-identical to the generic kernel's and to massiv's.
+#include <cstdlib>
+
 #include "mb_arith.cuh"
 #include "mb_internal.h"
 #include "mb_post.cuh"
@@ -32,10 +34,13 @@ struct SWProgram {
 };
 
 struct SWParams {
-  int in_h, in_w, out_h, out_w;
-  int shift_y, shift_x;  // source index of the window's first cell for output (0, 0)
-  int y0, y1;            // output rows produced
-  int tiles_x, ntiles;
+  int rank;              // 2, or 3: a tile is 32 x 128 cells of ONE output plane, its box carries the window's depth
+  int in_d, in_h, in_w, out_d, out_h, out_w;
+  int shift_z, shift_y, shift_x;  // source index of the window's first cell for output (0, 0, 0)
+  int o0, o1;            // outermost output range produced: rows (rank 2) or planes (rank 3)
+  int tiles_x, tiles_y, ntiles;
+  int bd, nstages;       // box depth (1 for rank 2); stages of the ring (3, or 2 when the boxes are large)
+  int min_dz;
   int border, use_tma, zero_fill_ok;
   int xoff;              // the window begins xoff elements into the staged row (boxes start on 16-byte boundaries)
   int bw, bh;            // staged box, elements (bw a multiple of the vector length)
@@ -145,46 +150,58 @@ __global__ void __launch_bounds__(256, 2)
 smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SWParams P, const T *__restrict__ in, T *__restrict__ out) {
   constexpr int V = 16 / (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + SW_S * P.stage_bytes);
+  const int S = P.nstages;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * P.stage_bytes);
   int *s_off = reinterpret_cast<int *>(full + 8);
   T *s_k = reinterpret_cast<T *>(s_off + ((P.ntaps + 3) & ~3));
   const int tid = threadIdx.x;
   if (tid == 0) {
     if (TMA) tma_prefetch_desc(&tmap);
-    for (int s = 0; s < SW_S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
-  const int pitch = P.bw;
+  const int pitch = P.bw, plane = P.bw * P.bh;
   // the tap table: shared-memory offset of every tap relative to a cell's window origin, and its coefficient
   for (int t = tid; t < P.ntaps; t += 256) {
-    s_off[t] = (P.taps[2 * t] - P.min_dy) * pitch + (P.taps[2 * t + 1] - P.min_dx) + P.xoff;
+    const int32_t *o = P.taps + P.rank * t;
+    const int dz = P.rank == 3 ? o[0] - P.min_dz : 0;
+    s_off[t] = dz * plane + (o[P.rank - 2] - P.min_dy) * pitch + (o[P.rank - 1] - P.min_dx) + P.xoff;
     s_k[t] = P.coef ? reinterpret_cast<const T *>(P.coef)[t] : T(0);
   }
   __syncthreads();
 
   const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_origin = [&](int i, int &oy0, int &ox0) {
+  // tiles run x fastest, then y, then (rank 3) the output plane: the planes a box shares with the tile one plane
+  // further are re-read out of L2 a few hundred tiles later
+  auto tile_origin = [&](int i, int &oz, int &oy0, int &ox0) {
     const int t = (int)blockIdx.x + i * (int)gridDim.x;
-    oy0 = P.y0 + (t / P.tiles_x) * SW_TH;
     ox0 = (t % P.tiles_x) * SW_TW;
+    const int rest = t / P.tiles_x;
+    if (P.rank == 3) {
+      oy0 = (rest % P.tiles_y) * SW_TH;
+      oz = P.o0 + rest / P.tiles_y;
+    } else {
+      oy0 = P.o0 + rest * SW_TH;
+      oz = 0;
+    }
   };
-  // may tile i be fetched by TMA?  yes when out-of-range cells are never used or zero is the border
-  auto inside = [&](int oy0, int ox0) -> bool {
-    const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
-    return by0 >= 0 && bx0 >= 0 && by0 + P.bh <= P.in_h && bx0 + P.bw <= P.in_w;
+  auto inside = [&](int oz, int oy0, int ox0) -> bool {
+    const int bz0 = oz + P.shift_z, by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
+    return bz0 >= 0 && by0 >= 0 && bx0 >= 0 && bz0 + P.bd <= P.in_d && by0 + P.bh <= P.in_h && bx0 + P.bw <= P.in_w;
   };
-  auto async_ok = [&](int oy0, int ox0) -> bool { return TMA && (P.zero_fill_ok || inside(oy0, ox0)); };
+  // every box comes by TMA (cells outside the array arrive as zeros); a box that crosses the array's edge under a
+  // border other than Fill 0 has its outside cells patched afterwards
   auto prefetch = [&](int i) {
     if (!TMA || tid != 0 || i >= my_tiles) return;
-    int oy0, ox0;
-    tile_origin(i, oy0, ox0);
-    if (!async_ok(oy0, ox0)) return;
-    const int s = i % SW_S;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(P.bw * P.bh * (int)sizeof(T)));
-    tma_load_2d(smem + s * P.stage_bytes, &tmap, &full[s], ox0 + P.shift_x - P.xoff, oy0 + P.shift_y);
+    int oz, oy0, ox0;
+    tile_origin(i, oz, oy0, ox0);
+    const int s = i % S;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(P.bw * P.bh * P.bd * (int)sizeof(T)));
+    if (P.rank == 3) tma_load_3d(smem + s * P.stage_bytes, &tmap, &full[s], ox0 + P.shift_x - P.xoff, oy0 + P.shift_y, oz + P.shift_z);
+    else tma_load_2d(smem + s * P.stage_bytes, &tmap, &full[s], ox0 + P.shift_x - P.xoff, oy0 + P.shift_y);
   };
 #pragma unroll 1
-  for (int i = 0; i < SW_S - 1; ++i) prefetch(i);
+  for (int i = 0; i < S - 1; ++i) prefetch(i);
   T fillv;
   {
     unsigned long long b = P.fill_bits;
@@ -195,30 +212,44 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const bool skip = P.skip_zero != 0;
 
   for (int i = 0; i < my_tiles; ++i) {
-    const int s = i % SW_S;
-    int oy0, ox0;
-    tile_origin(i, oy0, ox0);
-    if (TMA && tid == 0 && i + SW_S - 1 < my_tiles) fence_proxy_async();
-    prefetch(i + SW_S - 1);
+    const int s = i % S;
+    int oz, oy0, ox0;
+    tile_origin(i, oz, oy0, ox0);
+    if (TMA && tid == 0 && i + S - 1 < my_tiles) fence_proxy_async();
+    prefetch(i + S - 1);
     T *sm = reinterpret_cast<T *>(smem + s * P.stage_bytes);
-    const bool by_tma = async_ok(oy0, ox0);
-    if (by_tma) {
+    const bool all_in = inside(oz, oy0, ox0);
+    const bool patch = !(TMA && (all_in || P.zero_fill_ok));
+    if (TMA) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
-    } else {
-      // without a tensor map, or for a tile that crosses the array's edge under a border other than Fill 0: every
-      // box cell through the border rule (Core/Index.hs:236-253); cells inside the array need no resolution
-      const int by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
-      const bool all_in = inside(oy0, ox0);
-      for (int r = warp; r < P.bh; r += 8) {
-        int gy = by0 + r;
-        const bool row_ok = all_in || resolve_border32(P.border, P.in_h, gy);
-        const T *srow = in + (size_t)gy * P.in_w;
-        for (int c = lane; c < P.bw; c += 32) {
+    }
+    if (patch) {
+      // box cells through the border rule (Core/Index.hs:236-253).  After a TMA fetch only the cells outside the array
+      // are written: whole rows whose plane or row index is outside, else the columns left and right of the array.
+      const int bz0 = oz + P.shift_z, by0 = oy0 + P.shift_y, bx0 = ox0 + P.shift_x - P.xoff;
+      int cl = bx0 < 0 ? -bx0 : 0, cr = P.in_w - bx0;  // box columns [cl, cr) lie inside the array
+      if (cl > P.bw) cl = P.bw;
+      if (cr > P.bw) cr = P.bw;
+      if (cr < cl) cr = cl;
+      for (int rr = warp; rr < P.bh * P.bd; rr += 8) {
+        const int q = rr / P.bh, r = rr - q * P.bh;
+        int gz = bz0 + q, gy = by0 + r;
+        const bool row_in = (P.rank < 3 || (unsigned)gz < (unsigned)P.in_d) && (unsigned)gy < (unsigned)P.in_h;
+        const bool row_ok = row_in || ((P.rank < 3 || resolve_border32(P.border, P.in_d, gz)) && resolve_border32(P.border, P.in_h, gy));
+        const T *srow = in + ((size_t)(P.rank == 3 ? gz : 0) * P.in_h + gy) * P.in_w;
+        T *drow = sm + q * plane + r * pitch;
+        auto cell = [&](int c) {
           int gx = bx0 + c;
           T v = fillv;
-          if (row_ok && (all_in || resolve_border32(P.border, P.in_w, gx))) v = srow[gx];
-          sm[r * pitch + c] = v;
+          if (row_ok && resolve_border32(P.border, P.in_w, gx)) v = srow[gx];
+          drow[c] = v;
+        };
+        if (TMA && row_in) {
+          for (int c = lane; c < cl; c += 32) cell(c);
+          for (int c = cr + lane; c < P.bw; c += 32) cell(c);
+        } else {
+          for (int c = lane; c < P.bw; c += 32) cell(c);
         }
       }
       __syncthreads();
@@ -279,16 +310,16 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
       for (int r = 0; r < RP; ++r) {
         const int gy = oy0 + warp * SW_RY + r0 + r;
-        if (gy < P.y1) {
+        if (gy < (P.rank == 3 ? P.out_h : P.o1)) {
 #pragma unroll
           for (int c = 0; c < SW_CX; ++c) {
             const int gx = ox0 + lane + 32 * c;
-            if (gx < P.out_w) out[(size_t)gy * P.out_w + gx] = va[r][c];
+            if (gx < P.out_w) out[((size_t)oz * P.out_h + gy) * P.out_w + gx] = va[r][c];
           }
         }
       }
     }
-    if (TMA && !by_tma) fence_proxy_async();  // generic-proxy writes into the stage come before its next TMA refill
+    if (TMA && patch) fence_proxy_async();  // generic-proxy writes into the stage come before its next TMA refill
     __syncthreads();  // everyone is done with stage s before it is refilled
   }
 }
@@ -430,6 +461,8 @@ static bool build_program(const Plan &p, SWProgram *X, std::vector<uint8_t> *coe
   return g.ok;
 }
 
+constexpr size_t SW_SMEM_MAX = 227 * 1024;  // the opt-in limit of a CTA on sm_100
+
 template <typename T, bool CANON = false>
 static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void *d_coef, const void *d_taps2, const void *d_in, void *d_out,
                        const OuterRange *range) {
@@ -437,25 +470,31 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   const Plan &p = dp.p;
   SWParams P;
   std::memset(&P, 0, sizeof(P));
-  P.in_h = (int)p.in_dims[0]; P.in_w = (int)p.in_dims[1];
-  P.out_h = (int)p.out_dims[0]; P.out_w = (int)p.out_dims[1];
-  P.min_dy = (int)p.min_off[0]; P.min_dx = (int)p.min_off[1];
-  P.shift_y = (int)(p.shift[0] + p.min_off[0]); P.shift_x = (int)(p.shift[1] + p.min_off[1]);
-  P.y0 = range ? (int)range->o0 : 0;
-  P.y1 = range ? (int)range->o1 : P.out_h;
-  if (P.y1 <= P.y0) return MB_OK;
+  const int r = p.rank, iy = r - 2, ix = r - 1;
+  P.rank = r;
+  P.in_d = r == 3 ? (int)p.in_dims[0] : 1; P.in_h = (int)p.in_dims[iy]; P.in_w = (int)p.in_dims[ix];
+  P.out_d = r == 3 ? (int)p.out_dims[0] : 1; P.out_h = (int)p.out_dims[iy]; P.out_w = (int)p.out_dims[ix];
+  P.min_dz = r == 3 ? (int)p.min_off[0] : 0; P.min_dy = (int)p.min_off[iy]; P.min_dx = (int)p.min_off[ix];
+  P.shift_z = r == 3 ? (int)(p.shift[0] + p.min_off[0]) : 0;
+  P.shift_y = (int)(p.shift[iy] + p.min_off[iy]); P.shift_x = (int)(p.shift[ix] + p.min_off[ix]);
+  P.o0 = range ? (int)range->o0 : 0;
+  P.o1 = range ? (int)range->o1 : (int)p.out_dims[0];
+  if (P.o1 <= P.o0) return MB_OK;
   P.tiles_x = (P.out_w + SW_TW - 1) / SW_TW;
-  P.ntiles = P.tiles_x * ((P.y1 - P.y0 + SW_TH - 1) / SW_TH);
+  P.tiles_y = (P.out_h + SW_TH - 1) / SW_TH;
+  P.ntiles = r == 3 ? P.tiles_x * P.tiles_y * (P.o1 - P.o0) : P.tiles_x * ((P.o1 - P.o0 + SW_TH - 1) / SW_TH);
   P.border = p.border;
   std::memcpy(&P.fill_bits, p.fill, 8);
   bool fill_zero = p.border == MB_FILL;
   for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) fill_zero = false;
   P.zero_fill_ok = fill_zero;
-  const int wh = (int)(p.max_off[0] - p.min_off[0] + 1), ww = (int)(p.max_off[1] - p.min_off[1] + 1);
+  const int wd = r == 3 ? (int)(p.max_off[0] - p.min_off[0] + 1) : 1;
+  const int wh = (int)(p.max_off[iy] - p.min_off[iy] + 1), ww = (int)(p.max_off[ix] - p.min_off[ix] + 1);
   P.xoff = ((P.shift_x % V) + V) % V;
   P.bw = ((P.xoff + SW_TW + ww - 1 + V - 1) / V) * V;
   P.bh = SW_TH + wh - 1;
-  P.stage_bytes = ((P.bw * P.bh * (int)sizeof(T) + 127) / 128) * 128;
+  P.bd = wd;
+  P.stage_bytes = ((P.bw * P.bh * P.bd * (int)sizeof(T) + 127) / 128) * 128;
   P.ntaps = (int)p.ntaps * (p.kind == MB_MAG2 ? 2 : 1);
   P.bool_canon = p.elem == MB_BOOL32;
   P.skip_zero = (p.flags & MB_FLAG_ASSUME_FINITE) != 0;
@@ -465,14 +504,20 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   P.X = X;
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
-  const uint32_t box[2] = {(uint32_t)P.bh, (uint32_t)P.bw};
-  P.use_tma = (!c->no_tma && P.bw <= 256 && P.bh <= 256 && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box)) ? 1 : 0;
-  const size_t smem_bytes = (size_t)SW_S * P.stage_bytes + 64 + (size_t)((P.ntaps + 3) & ~3) * 4 + (size_t)P.ntaps * sizeof(T) + 16;
-  if (smem_bytes > 200 * 1024) return -1;
+  const uint32_t box2[2] = {(uint32_t)P.bh, (uint32_t)P.bw}, box3[3] = {(uint32_t)P.bd, (uint32_t)P.bh, (uint32_t)P.bw};
+  P.use_tma = (!c->no_tma && P.bw <= 256 && P.bh <= 256 && P.bd <= 256 &&
+               make_tensor_map(&tmap, p.elem, p.esize, r, d_in, p.in_dims, r == 3 ? box3 : box2)) ? 1 : 0;
+  // three stages when they fit, two for large boxes (deep windows, 8-byte elements)
+  const size_t tables = 64 + (size_t)((P.ntaps + 3) & ~3) * 4 + (size_t)P.ntaps * sizeof(T) + 16;
+  P.nstages = SW_S;
+  if (const char *e = std::getenv("MASSIV_B200_SW_STAGES")) P.nstages = std::atoi(e) == 2 ? 2 : 3;  // measurement knob
+  if ((size_t)P.nstages * P.stage_bytes + tables > 200 * 1024) P.nstages = 2;  // (three stages leave room for L1)
+  const size_t smem_bytes = (size_t)P.nstages * P.stage_bytes + tables;
+  if (smem_bytes > SW_SMEM_MAX) return -1;
   auto kern = P.use_tma ? smallwin_kernel<T, true, CANON> : smallwin_kernel<T, false, CANON>;
   static bool configured[64][2] = {{false}};  // (per instantiation: T, CANON)
   if (!configured[c->device & 63][P.use_tma]) {
-    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));
     configured[c->device & 63][P.use_tma] = true;
   }
   int occ = 0;
@@ -487,14 +532,15 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   return check_cuda(c, cudaGetLastError(), "smallwin_kernel launch");
 }
 
-// -1: not a rank-2, unit-stride, small-window plan
+// -1: not a rank-2 / rank-3, unit-stride, small-window plan
 int launch_smallwin(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
   const Plan &p = dp.p;
-  if (p.rank != 2 || !p.unit_stride() || p.ntaps < 1) return -1;
-  if (p.in_dims[0] < 1 || p.in_dims[1] < 1) return -1;
-  if (p.in_dims[0] >= (1ll << 30) || p.in_dims[1] >= (1ll << 30) || p.out_dims[0] >= (1ll << 30) || p.out_dims[1] >= (1ll << 30)) return -1;
-  if (p.out_elems < c->tile_min_elems) return -1;
-  if (p.max_off[0] - p.min_off[0] + 1 > SW_MAX_WIN || p.max_off[1] - p.min_off[1] + 1 > SW_MAX_WIN) return -1;
+  if ((p.rank != 2 && p.rank != 3) || !p.unit_stride() || p.ntaps < 1) return -1;
+  for (int i = 0; i < p.rank; ++i) {
+    if (p.in_dims[i] < 1 || p.in_dims[i] >= (1ll << 30) || p.out_dims[i] >= (1ll << 30)) return -1;
+    if (p.max_off[i] - p.min_off[i] + 1 > SW_MAX_WIN) return -1;
+  }
+  if (p.out_elems < c->tile_min_elems || p.out_elems >= (1ll << 40)) return -1;
   if (p.ntaps * (p.kind == MB_MAG2 ? 2 : 1) > SW_MAX_TAPS) return -1;
   if (p.post.size() + p.prog.size() + 8 > sizeof(SWProgram::op)) return -1;
   SWProgram X;
@@ -505,7 +551,7 @@ int launch_smallwin(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
   const void *d_coef = dp.d_c1;
   const void *d_taps = dp.d_taps;
   if (p.kind == MB_MAG2) {
-    const size_t tb = (size_t)p.ntaps * 2 * sizeof(int32_t), cb = coef.size();
+    const size_t tb = (size_t)p.ntaps * p.rank * sizeof(int32_t), cb = coef.size();
     if (!dp.d_sw) {
       std::vector<uint8_t> host(2 * tb + cb);
       std::memcpy(host.data(), p.tap_off.data(), tb);

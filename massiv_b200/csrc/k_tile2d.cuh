@@ -62,7 +62,13 @@ template <typename T, int OP, bool REV, int KH, int KW, int XOFF> struct T2Cfg {
   static constexpr int NV = 1 + HALO / V;
   static constexpr int BW = TW + HALO, BH = TH + KH - 1;
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
-  static constexpr int S = 4;
+  // ring depth: 8-byte elements are DRAM-bound and gain from residency (two stages: six CTAs per SM instead of three —
+  // avg3x3 Double 16384^2: S = 2: 338 Gcells/s, 3: 311, 4: 308); the 4-byte kernels are issue-bound and want the deeper
+  // prefetch (Sobel Float 32768^2: S = 4: 585, 3: 545, 2: 553)
+#ifndef MB_T2_S
+#define MB_T2_S (sizeof(T) == 8 ? 2 : 4)
+#endif
+  static constexpr int S = MB_T2_S;
   static constexpr int SMEM = S * STAGE + 64;
 };
 

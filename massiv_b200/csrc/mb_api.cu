@@ -169,7 +169,8 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
     // behind the compile-time-shaped kernels they are a second pass over the output.  Measured (scripts/probe_post.py,
     // 16384^2): conv 3x3 |.|*c Float 384 vs 218 Gcells/s, avg 3x3 + c Double 218 vs 123, conv 5x5 sqrt|.| Float 206 vs 181;
     // without maps the shaped kernels win (563 vs 538, 605 vs 504, 396 vs 259).
-    if (c->prefer_smallwin || (!dp.p.post.empty() && dp.p.ntaps <= 32)) {
+    // (rank 2 only: the rank-3 small-window path re-stages a box per output plane and loses to vol3d + a post pass)
+    if (c->prefer_smallwin || (!dp.p.post.empty() && dp.p.ntaps <= 32 && dp.p.rank == 2)) {
       st = launch_smallwin(c, dp, d_in, d_out, range);
       if (st != -1) return st;
     }
@@ -181,9 +182,9 @@ static int launch_family(Ctx *c, const DevPlan &dp, const void *d_in, void *d_ou
     if (st != -1) return st;
     st = launch_direct2d(c, dp, d_in, d_out, range);
     if (st != -1) return st;
-    st = launch_smallwin(c, dp, d_in, d_out, range);
+    st = launch_batched(c, dp, d_in, d_out, range);  // (stacks of slices keep the rank-2 kernels' speed)
     if (st != -1) return st;
-    st = launch_batched(c, dp, d_in, d_out, range);
+    st = launch_smallwin(c, dp, d_in, d_out, range);
     if (st != -1) return st;
   }
   return launch_generic(c, dp, d_in, d_out, range);

@@ -42,5 +42,25 @@ def main(rep):
             pass
 
 
+def opcode_mix(rep, top=14):
+    """executed warp-instructions by opcode (source page; needs -lineinfo / --import-source) and per output cell if given"""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(line for line in raw.splitlines() if line.startswith('"')))
+    if len(rows) < 3:
+        return
+    hdr = rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    if "Instructions Executed" not in ix:
+        return
+    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    total = sum(int(r[ix["Instructions Executed"]]) for r in data)
+    mix = {}
+    for r in data:
+        op = [o for o in r[ix["Source"]].split() if not o.startswith("@")][0]
+        mix[op] = mix.get(op, 0) + int(r[ix["Instructions Executed"]])
+    print(f"  executed warp-instructions {total}: " + ", ".join(f"{op} {100 * n / total:.1f}%" for op, n in sorted(mix.items(), key=lambda t: -t[1])[:top]))
+
+
 if __name__ == "__main__":
     main(sys.argv[1])
+    opcode_mix(sys.argv[1])

@@ -88,3 +88,36 @@ def test_closure_form_sobel_of_the_reference_benchmark(dev):
         got = M.compute(M.mapStencil(M.Edge, op, dev.fromHost(a))).toHost()
         assert bits_equal(got, want)
         assert dev.last_kernel == "smallwin", dev.last_kernel
+
+
+@pytest.mark.parametrize("dtname", ["float32", "float64", "uint8", "int64"])
+def test_small_window_kernel_rank3(dev, dtname):
+    """3-D folds, windows other than 3x3x3, 3-D expressions: a tile is one output plane whose box carries the window's depth"""
+    dt = np.dtype(dtname)
+    rng = np.random.default_rng(zlib.crc32(("r3" + dtname).encode()))
+    dev.set_option("force_generic", 0)
+    dev.set_option("tile_min_elems", 0)
+    for shape in ((20, 40, 300), (7, 70, 131)):
+        arr = (rng.standard_normal(shape) if dt.kind == "f" else rng.integers(-9 if dt.kind == "i" else 0, 10, shape)).astype(dt)
+        k234 = (rng.standard_normal((2, 3, 4)) if dt.kind == "f" else rng.integers(0, 3, (2, 3, 4))).astype(dt)
+        k511 = (rng.standard_normal((5, 1, 1)) if dt.kind == "f" else rng.integers(0, 3, (5, 1, 1))).astype(dt)
+        cases = [M.sumStencil(M.Sz(3, 3, 3)), M.makeCorrelationStencilFromKernel(k234), M.makeConvolutionStencilFromKernel(k511),
+                 M.productStencil(M.Sz(2, 2, 2)), M.sumStencil(M.Sz(3, 3, 3)) - M.makeConvolutionStencilFromKernel(k234) * 2,
+                 abs(M.makeCorrelationStencilFromKernel(k234) - M.sumStencil(M.Sz(1, 2, 2)))]
+        if dt.kind == "f":
+            cases.append(M.avgStencil(M.Sz(3, 3, 3)))
+        else:
+            cases.append(M.maxStencil(M.Sz(3, 2, 3)))
+        for i, st in enumerate(cases):
+            for border in (M.Fill(dt.type(1)), M.Fill(dt.type(0)), M.Wrap, M.Continue):
+                want, _ = oracle_of_dw(M.mapStencil(border, st, arr), arr)
+                got = M.compute(M.mapStencil(border, st, dev.fromHost(arr))).toHost()
+                assert bits_equal(got, want), (shape, i, border, dev.last_kernel)
+                # (a 5-plane box of 8-byte elements does not fit two stages of shared memory: the generic kernel takes it)
+                assert dev.last_kernel == "smallwin" or (dt.itemsize == 8 and i == 2), (dev.last_kernel, shape, i)
+        # iterated: a 3-D fold step
+        want = arr
+        for _ in range(3):
+            want, _ = oracle_of_dw(M.mapStencil(M.Edge, cases[0] if dt.kind != "f" else cases[-1], want), want)
+        got = M.iterateStencil(3, M.Edge, cases[0] if dt.kind != "f" else cases[-1], dev.fromHost(arr)).toHost()
+        assert bits_equal(got, want)
