@@ -44,6 +44,7 @@ struct SWParams {
   int border, use_tma, zero_fill_ok;
   int xoff;              // the window begins xoff elements into the staged row (boxes start on 16-byte boundaries)
   int bw, bh;            // staged box, elements (bw a multiple of the vector length)
+  int wused;             // columns [xoff, wused) of a staged row are read
   int stage_bytes;
   int ntaps;             // all terms together
   int bool_canon, skip_zero, trivial;  // trivial: one term, no program beyond it
@@ -173,8 +174,16 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // tiles run x fastest, then y, then (rank 3) the output plane: the planes a box shares with the tile one plane
   // further are re-read out of L2 a few hundred tiles later
+  // Within wave i (gridDim.x consecutive tiles) CTA b takes tile (b + i) mod gridDim.x: the tiles on the array's rim,
+  // which cost a patch, would otherwise fall to the same few CTAs every wave (148 = 4 mod 8 tiles per row).
+  const int full_waves = P.ntiles / (int)gridDim.x;
   auto tile_origin = [&](int i, int &oz, int &oy0, int &ox0) {
-    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    int slot = (int)blockIdx.x;
+    if (i < full_waves) {
+      slot += i % (int)gridDim.x;
+      if (slot >= (int)gridDim.x) slot -= (int)gridDim.x;
+    }
+    const int t = slot + i * (int)gridDim.x;
     ox0 = (t % P.tiles_x) * SW_TW;
     const int rest = t / P.tiles_x;
     if (P.rank == 3) {
@@ -232,24 +241,31 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       if (cl > P.bw) cl = P.bw;
       if (cr > P.bw) cr = P.bw;
       if (cr < cl) cr = cl;
+      auto cell = [&](int q, int r, int c, int gz, int gy, bool row_ok) {
+        int gx = bx0 + c;
+        T v = fillv;
+        if (row_ok && resolve_border32(P.border, P.in_w, gx)) v = in[((size_t)(P.rank == 3 ? gz : 0) * P.in_h + gy) * P.in_w + gx];
+        sm[q * plane + r * pitch + c] = v;
+      };
+      // whole rows: all of them without TMA, else those whose plane or row index is outside
       for (int rr = warp; rr < P.bh * P.bd; rr += 8) {
         const int q = rr / P.bh, r = rr - q * P.bh;
         int gz = bz0 + q, gy = by0 + r;
         const bool row_in = (P.rank < 3 || (unsigned)gz < (unsigned)P.in_d) && (unsigned)gy < (unsigned)P.in_h;
+        if (TMA && row_in) continue;
         const bool row_ok = row_in || ((P.rank < 3 || resolve_border32(P.border, P.in_d, gz)) && resolve_border32(P.border, P.in_h, gy));
-        const T *srow = in + ((size_t)(P.rank == 3 ? gz : 0) * P.in_h + gy) * P.in_w;
-        T *drow = sm + q * plane + r * pitch;
-        auto cell = [&](int c) {
-          int gx = bx0 + c;
-          T v = fillv;
-          if (row_ok && resolve_border32(P.border, P.in_w, gx)) v = srow[gx];
-          drow[c] = v;
-        };
-        if (TMA && row_in) {
-          for (int c = lane; c < cl; c += 32) cell(c);
-          for (int c = cr + lane; c < P.bw; c += 32) cell(c);
-        } else {
-          for (int c = lane; c < P.bw; c += 32) cell(c);
+        for (int c = lane; c < P.bw; c += 32) cell(q, r, c, gz, gy, row_ok);
+      }
+      if (TMA) {
+        // the columns left and right of the array in the rows inside it, one cell per thread and trip
+        const int l0 = P.xoff < cl ? P.xoff : cl, r1 = P.wused > cr ? P.wused : cr;
+        const int nl = cl - l0, nc = nl + (r1 - cr);
+        for (int item = tid; item < nc * P.bh * P.bd; item += 256) {
+          const int rr = item / nc, k = item - rr * nc;
+          const int q = rr / P.bh, r = rr - q * P.bh;
+          const int gz = bz0 + q, gy = by0 + r;
+          const bool row_in = (P.rank < 3 || (unsigned)gz < (unsigned)P.in_d) && (unsigned)gy < (unsigned)P.in_h;
+          if (row_in) cell(q, r, k < nl ? l0 + k : cr + (k - nl), gz, gy, true);
         }
       }
       __syncthreads();
@@ -493,6 +509,7 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   P.xoff = ((P.shift_x % V) + V) % V;
   P.bw = ((P.xoff + SW_TW + ww - 1 + V - 1) / V) * V;
   P.bh = SW_TH + wh - 1;
+  P.wused = P.xoff + SW_TW + ww - 1;
   P.bd = wd;
   P.stage_bytes = ((P.bw * P.bh * P.bd * (int)sizeof(T) + 127) / 128) * 128;
   P.ntaps = (int)p.ntaps * (p.kind == MB_MAG2 ? 2 : 1);
@@ -510,18 +527,28 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   // three stages when they fit, two for large boxes (deep windows, 8-byte elements)
   const size_t tables = 64 + (size_t)((P.ntaps + 3) & ~3) * 4 + (size_t)P.ntaps * sizeof(T) + 16;
   P.nstages = SW_S;
-  if (const char *e = std::getenv("MASSIV_B200_SW_STAGES")) P.nstages = std::atoi(e) == 2 ? 2 : 3;  // measurement knob
   if ((size_t)P.nstages * P.stage_bytes + tables > 200 * 1024) P.nstages = 2;  // (three stages leave room for L1)
-  const size_t smem_bytes = (size_t)P.nstages * P.stage_bytes + tables;
-  if (smem_bytes > SW_SMEM_MAX) return -1;
+  if ((size_t)P.nstages * P.stage_bytes + tables > SW_SMEM_MAX) return -1;
   auto kern = P.use_tma ? smallwin_kernel<T, true, CANON> : smallwin_kernel<T, false, CANON>;
   static bool configured[64][2] = {{false}};  // (per instantiation: T, CANON)
   if (!configured[c->device & 63][P.use_tma]) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));
     configured[c->device & 63][P.use_tma] = true;
   }
+  // residency before ring depth: two stages when that lets another CTA onto the SM (rank-3 boxes carry the window's
+  // depth: avg 3x3x3 Float 1024^3 runs two CTAs of two stages, not one of three)
   int occ = 0;
-  MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
+  MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, (size_t)P.nstages * P.stage_bytes + tables));
+  if (P.nstages == 3) {
+    int occ2 = 0;
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, 256, (size_t)2 * P.stage_bytes + tables));
+    if (occ2 > occ) { occ = occ2; P.nstages = 2; }
+  }
+  if (const char *e = std::getenv("MASSIV_B200_SW_STAGES")) {  // measurement knob
+    P.nstages = std::atoi(e) == 2 ? 2 : P.nstages;
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, (size_t)P.nstages * P.stage_bytes + tables));
+  }
+  const size_t smem_bytes = (size_t)P.nstages * P.stage_bytes + tables;
   if (occ < 1) occ = 1;
   int grid = c->num_sms * occ;
   if (grid > P.ntiles) grid = P.ntiles;
