@@ -44,6 +44,14 @@ template <typename T, int K, int XOFF> struct S2Cfg {
 #endif
   static constexpr int S = MB_S2_S;
   static constexpr int SMEM = S * STAGE + TBUF + 64;
+  // arrays without a tensor map, 4-byte elements: boxes go through registers (k_tile2d.cuh); the box is only read by
+  // the row pass, so ONE stage does
+  static constexpr int RS_ROWS = (BH + 7) / 8, RS_COLS = (BW + 31) / 32;
+#ifndef MB_S2_REGSTAGE
+#define MB_S2_REGSTAGE 1
+#endif
+  static constexpr bool REGSTAGE = MB_S2_REGSTAGE && sizeof(T) == 4 && RS_ROWS * RS_COLS <= 36;
+  static constexpr int SMEM_RS = STAGE + TBUF + 64;
 };
 
 template <typename T, bool REV, int K, int XOFF, bool TMA>
@@ -54,13 +62,15 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
   using A = Arith<T>;
   constexpr int V = C::V, R = C::R, NVV = C::NV * V;
   extern __shared__ __align__(128) unsigned char smem[];
-  T *tbuf = reinterpret_cast<T *>(smem + C::S * C::STAGE);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::S * C::STAGE + C::TBUF);
+  constexpr bool RS = C::REGSTAGE && !TMA;
+  constexpr int NS = RS ? 1 : C::S;
+  T *tbuf = reinterpret_cast<T *>(smem + NS * C::STAGE);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + NS * C::STAGE + C::TBUF);
   const int tid = threadIdx.x;
   if (tid == 0) {
     if (TMA) tma_prefetch_desc(&tmap);
 #pragma unroll
-    for (int s = 0; s < C::S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -96,6 +106,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
       if (tid == 0 && i < my_tiles) issue(i);
       return;
     }
+    if (RS) return;
     if (i < my_tiles) {
       int oy0, ox0;
       tile_origin(i, oy0, ox0);
@@ -107,6 +118,36 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     }
     cp_async_commit();
   };
+  // register staging: tile i's box is held in stg from one trip to the next
+  T stg[RS ? C::RS_ROWS : 1][RS ? C::RS_COLS : 1];
+  auto rs_load = [&](int i) {
+    if (!RS || i >= my_tiles) return;
+    int oy0, ox0;
+    tile_origin(i, oy0, ox0);
+    if (!box_inside(oy0, ox0)) return;
+    const T *src = in + (size_t)(oy0 + P.shift_y + (tid >> 5)) * P.w + (ox0 + P.shift_x - XOFF) + (tid & 31);
+#pragma unroll
+    for (int k = 0; k < C::RS_ROWS; ++k) {
+      if (k * 8 + 8 <= C::BH || (tid >> 5) + k * 8 < C::BH) {
+#pragma unroll
+        for (int j = 0; j < C::RS_COLS; ++j)
+          if (j * 32 + 32 <= C::BW || (tid & 31) + j * 32 < C::BW) stg[k][j] = __ldg(src + (size_t)k * 8 * P.w + j * 32);
+      }
+    }
+  };
+  auto rs_store = [&](T *sm) {
+    if (!RS) return;
+    T *dst = sm + (tid >> 5) * C::BW + (tid & 31);
+#pragma unroll
+    for (int k = 0; k < C::RS_ROWS; ++k) {
+      if (k * 8 + 8 <= C::BH || (tid >> 5) + k * 8 < C::BH) {
+#pragma unroll
+        for (int j = 0; j < C::RS_COLS; ++j)
+          if (j * 32 + 32 <= C::BW || (tid & 31) + j * 32 < C::BW) dst[k * 8 * C::BW + j * 32] = stg[k][j];
+      }
+    }
+  };
+  if (RS) rs_load(0);
 #pragma unroll 1
   for (int i = 0; i < C::S - 1; ++i) prefetch(i);
   T fillv;
@@ -119,7 +160,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
   uint32_t phase = 0;
 
   for (int i = 0; i < my_tiles; ++i) {
-    const int s = i % C::S;
+    const int s = RS ? 0 : i % C::S;
     int oy0, ox0;
     tile_origin(i, oy0, ox0);
     if (TMA && tid == 0 && i + C::S - 1 < my_tiles) fence_proxy_async();
@@ -130,6 +171,10 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
     if (by_tma) {
       mbar_wait(&full[s], (phase >> s) & 1u);
       phase ^= 1u << s;
+    } else if (RS && box_inside(oy0, ox0)) {
+      rs_store(sm);
+      __syncthreads();
+      rs_load(i + 1);
     } else if (!TMA && box_inside(oy0, ox0)) {
       cp_async_wait_group<C::S - 1>();
       __syncthreads();
@@ -143,6 +188,7 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
         sm[e] = v;
       }
       __syncthreads();
+      rs_load(i + 1);
     }
 
     // ---- pass 1: 1 x K along the rows of the box, result rounded to T into tbuf ----
@@ -227,6 +273,9 @@ sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const S
         }
       }
     }
+    // (register staging: the stage is free after the barrier between the passes, tbuf after the one that follows
+    // the next fill)
+    if (RS) continue;
     if (!by_tma) fence_proxy_async();
     __syncthreads();  // stage s and tbuf are free again
   }
@@ -265,14 +314,15 @@ static int launch_s2(Ctx *c, const Plan &p1, const Plan &p2, const void *d_in, v
   auto kern = P.use_tma ? kern_tma : kern_cp;
   static int occ_dev[64][2] = {{0}};
   int &occ = occ_dev[c->device & 63][P.use_tma];
+  const int smem_bytes = (!P.use_tma && C::REGSTAGE) ? C::SMEM_RS : C::SMEM;
   if (occ == 0) {
-    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
+    MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
     if (occ < 1) occ = 1;
   }
   int grid = c->num_sms * occ;
   if (grid > P.ntiles) grid = P.ntiles;
-  kern<<<grid, 256, C::SMEM, c->stream>>>(tmap, P, CO, (const T *)d_in, (T *)d_out);
+  kern<<<grid, 256, smem_bytes, c->stream>>>(tmap, P, CO, (const T *)d_in, (T *)d_out);
   c->launches++;
   c->last_kernel = "sep2d";
   return check_cuda(c, cudaGetLastError(), "sep2d_kernel launch");

@@ -23,6 +23,7 @@ enum { V3_STAR7 = 0, V3_DENSE27 = 1 };
 
 struct V3Params {
   int in_d, in_h, in_w, out_d, out_h, out_w;
+  int in_pitch, out_pitch;  // row pitches in elements (in_w / out_w unless that array is padded: Ctx::in_pitch, out_pitch)
   int sz, sy, sx;  // source index of the window centre for output (0,0,0)
   int z0, z1;      // output planes produced
   int tiles_x, tiles_y, zc, nitems;
@@ -135,7 +136,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
     if (!TMA) {  // one commit group per load, empty when the box goes through the border rule at acquire time
       if (cp_ok(zsrc, oy0, ox0)) {
         // a warp per box row, the widest copies the row's alignment allows; zeros outside the array (mb_tma.cuh)
-        const T *pl = (zsrc >= 0 && zsrc < P.in_d) ? in + (size_t)zsrc * P.in_h * P.in_w : nullptr;
+        const T *pl = (zsrc >= 0 && zsrc < P.in_d) ? in + (size_t)zsrc * P.in_h * P.in_w : nullptr;  // (dense arrays only)
         stage_box<T, C::BH, C::BW, 8>(reinterpret_cast<T *>(smem + s * C::STAGE), pl, in, P.in_h, P.in_w, oy0 + P.sy - 1, ox0 + P.sx - V, tid);
       }
       cp_async_commit();
@@ -179,7 +180,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
         int gy = y0 + r, gx = x0 + c;
         T v = fillv;
         if (zin && resolve_border32(P.border, P.in_h, gy) && resolve_border32(P.border, P.in_w, gx))
-          v = in[((size_t)gz * P.in_h + gy) * P.in_w + gx];
+          v = in[((size_t)gz * P.in_h + gy) * P.in_pitch + gx];
         sm[e] = v;
       }
       fence_proxy_async();
@@ -254,7 +255,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
           }
           const int gy = oy0 + ly + r, gx = ox0 + lx;
           if (gy < P.out_h && gx < P.out_w) {
-            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_w + gx;
+            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_pitch + gx;
             if (P.vec_store && gx + V <= P.out_w) {
               uint4 q;
               memcpy(&q, res, 16);
@@ -326,7 +327,7 @@ vol3d_kernel(const __grid_constant__ CUtensorMap tmap, const V3Params P, const C
           }
           const int gy = oy0 + ly + r, gx = ox0 + lx;
           if (gy < P.out_h && gx < P.out_w) {
-            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_w + gx;
+            T *dst = out + ((size_t)gz * P.out_h + gy) * P.out_pitch + gx;
             if (P.vec_store && gx + V <= P.out_w) {
               uint4 q;
               memcpy(&q, res, 16);
@@ -377,13 +378,16 @@ static int launch_v3(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, c
   bool fill_zero = p.border == MB_FILL;
   for (int i = 0; i < p.esize; ++i) if (p.fill[i] != 0) fill_zero = false;
   P.zero_fill_ok = fill_zero;
-  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.out_w * sizeof(T)) % 16 == 0;
+  P.in_pitch = c->in_pitch ? (int)c->in_pitch : P.in_w;
+  P.out_pitch = c->out_pitch ? (int)c->out_pitch : P.out_w;
+  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.out_pitch * sizeof(T)) % 16 == 0;
   Coef27<T> K;
   std::memcpy(K.k, p.c1.data(), sizeof(T) * 27);
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
-  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
+  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box, c->in_pitch)) ? 1 : 0;
+  if (c->in_pitch && !P.use_tma) return fail(c, MB_ERR_UNSUPPORTED, "internal: padded arrays need a tensor map");
   auto kern_tma = vol3d_kernel<T, MODE, REV, DETECT, true>;
   auto kern_cp = vol3d_kernel<T, MODE, REV, DETECT, false>;
   auto kern = P.use_tma ? kern_tma : kern_cp;

@@ -42,6 +42,8 @@ struct TB2Params {
   int z0, z1;            // result planes produced
   int tiles_x, tiles_y, zc, nitems;
   int vec_store;
+  int pitch;             // row pitch in elements of the OUTPUT array (in_w unless it is padded: Ctx::out_pitch; a padded
+                         // input is described by the tensor map)
   int use_tma;           // 0: the array cannot be described to TMA; boxes are staged with cp.async (zero fill by hand)
 };
 
@@ -59,6 +61,17 @@ template <typename T, int R_> struct TB2Cfg {
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
   static constexpr int S = MB_TB2_S;
   static constexpr int SMEM = (S + 2) * STAGE + 128;    // S source stages + 2 intermediate planes + barriers + the producer's books
+  // Arrays without a tensor map, 8-byte elements: every box row comes through the bulk-copy engine from the 16-byte
+  // boundary at or one element before its first cell, so a row may sit ONE ELEMENT to the right in its (one vector
+  // wider) shared-memory row; the readers add that element to the row's address.  For 8-byte elements a shifted row
+  // costs the same shared-memory wavefronts (two LDS.64 instead of one LDS.128).
+#ifndef MB_TB2_BULK
+#define MB_TB2_BULK 1
+#endif
+  static constexpr bool BULK = MB_TB2_BULK && sizeof(T) == 8;
+  static constexpr int SP_NT = BULK ? BW + V : BW;
+  static constexpr int STAGE_NT = ((SP_NT * BH * (int)sizeof(T) + 127) / 128) * 128;
+  static constexpr int SMEM_NT = S * STAGE_NT + 2 * STAGE + 128;
 };
 
 template <typename T> __device__ __forceinline__ void lds_v(T *dst, const T *src) {
@@ -189,8 +202,9 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   Finite2 bad;
   using C = TB2Cfg<T, R_>;
   constexpr int V = C::V, R = C::R, S = C::S, BW = C::BW;
-  constexpr int SP = C::BW;         // row pitch of a staged source plane
-  constexpr int SSTAGE = C::STAGE;  // bytes per source stage
+  constexpr bool BULK = !TMA && C::BULK;
+  constexpr int SP = TMA ? C::BW : C::SP_NT;         // row pitch of a staged source plane
+  constexpr int SSTAGE = TMA ? C::STAGE : C::STAGE_NT;  // bytes per source stage
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *const ubase = smem + S * SSTAGE;  // two intermediate planes (row pitch BW), STAGE bytes apart
   uint64_t *full = reinterpret_cast<uint64_t *>(ubase + 2 * C::STAGE);
@@ -226,10 +240,10 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   // With TMA only thread 0 produces: its books live in shared memory so that they do not occupy registers in
   // every thread of a kernel that sits at the 128-register limit.  (Without TMA every thread copies and keeps
   // them in registers.)
-  struct Books { int it, left, x, y, z, issued, total; };
+  struct Books { int it, left, x, y, z, issued, total, code; };
   Books *const pb = reinterpret_cast<Books *>(ufree + 2);
   constexpr bool BOOKS_SMEM = TMA && MB_TB2_BOOKS_SMEM;
-  Books rb = {0, 0, 0, 0, 0, 0, 0};
+  Books rb = {0, 0, 0, 0, 0, 0, 0, -1};
   if (tid == 0 || !TMA) {
     for (int it = 0; it < my_items; ++it) {
       int a, nz, b, c;
@@ -238,6 +252,22 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     }
     if (BOOKS_SMEM) *pb = rb;
   }
+  // May the box of plane z at (y, x) come through the bulk-copy engine?  It must lie inside the array, and not end with
+  // the array's last row (a shifted row reads one element past its end).  The in-plane part of the answer and the
+  // parity of the box's first element are taken once per item (xy_code: -1 no, else the parity of plane 0's box);
+  // row r of plane z's box is shifted when (parity + z * (H * W & 1) + r * (W & 1)) is odd.
+  const unsigned base_el = (unsigned)(reinterpret_cast<uintptr_t>(in) / sizeof(T));
+  const int hw1 = (P.in_h & P.in_w) & 1, sb = P.in_w & 1;
+  auto xy_code = [&](int y, int x) -> int {
+    if (!BULK || y < 0 || y + C::BH > P.in_h || x < 0 || x + C::BW > P.in_w) return -1;
+    return (int)((base_el + (unsigned)y * (unsigned)P.in_w + (unsigned)x) & 1u) | (y + C::BH == P.in_h ? 2 : 0);
+  };
+  auto bulk_plane = [&](int code, int z, int &sa) -> bool {
+    sa = 0;
+    if (!BULK || code < 0 || z < 0 || z >= P.in_d || ((code & 2) && z == P.in_d - 1)) return false;
+    sa = (code + (z & hw1)) & 1;
+    return true;
+  };
   auto issue_upto = [&](int limit) {  // limit = planes released so far + S
     Books q = BOOKS_SMEM ? *pb : rb;
     while (q.issued < q.total && q.issued < limit) {
@@ -246,17 +276,37 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
         item_geom(q.it++, oz0, nz, oy0, ox0);
         q.left = nz + 4;
         q.x = ox0 - 2 * V; q.y = oy0 - 2; q.z = oz0 + P.sz2 - 2;
+        q.code = xy_code(q.y, q.x);
       }
       const int s = q.issued % S;
       if (TMA) {
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
         tma_load_3d(smem + s * SSTAGE, &tmap, &full[s], q.x, q.y, q.z);
       } else {
-        // the whole CTA copies the box, a warp per row with the widest copies the row's alignment allows; cells
-        // outside the array become zeros, as with TMA (mb_tma.cuh).  One commit group per plane.
-        const T *pl = (q.z >= 0 && q.z < P.in_d) ? in + (size_t)q.z * P.in_h * P.in_w : nullptr;
-        stage_box<T, C::BH, C::BW, MB_TB2_NW>(reinterpret_cast<T *>(smem + s * SSTAGE), pl, in, P.in_h, P.in_w, q.y, q.x, tid);
-        cp_async_commit();
+        int sa;
+        if (BULK && bulk_plane(q.code, q.z, sa)) {
+          // a box inside the array: one bulk copy per row, (shifted rows are 16 bytes
+          // longer: the element before and the element after travel too)
+          if (tid == 0) {
+            const int nsh = sb ? (C::BH + sa) / 2 : sa * C::BH;  // rows r < BH with (sa + sb * r) odd
+            mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)) + 16u * (uint32_t)nsh);
+          }
+          // (the copy instruction takes its operands from uniform registers: a warp issues its lanes' copies one
+          // after the other, so the rows are dealt out over all warps, a few lanes each)
+          const int row = (tid >> 5) + MB_TB2_NW * (tid & 31);
+          if ((tid & 31) < (C::BH + MB_TB2_NW - 1) / MB_TB2_NW && row < C::BH) {
+            fence_proxy_async();  // the stage's last readers (generic proxy) come before the engine's writes
+            const int sh = (sa + sb * row) & 1;
+            const T *src = in + ((size_t)q.z * P.in_h + (q.y + row)) * P.in_w + q.x - sh;
+            bulk_load_1d(smem + s * SSTAGE + (size_t)row * SP * sizeof(T), src, (uint32_t)(C::BW * sizeof(T)) + 16u * (uint32_t)sh, &full[s]);
+          }
+        } else {
+          // the whole CTA copies the box, a warp per row with the widest copies the row's alignment allows; cells
+          // outside the array become zeros, as with TMA (mb_tma.cuh).
+          const T *pl = (q.z >= 0 && q.z < P.in_d) ? in + (size_t)q.z * P.in_h * P.in_w : nullptr;
+          stage_box<T, C::BH, C::BW, MB_TB2_NW, SP>(reinterpret_cast<T *>(smem + s * SSTAGE), pl, in, P.in_h, P.in_w, q.y, q.x, tid);
+        }
+        cp_async_commit();  // one commit group per plane (empty for a bulk plane: the counts stay in step)
       }
       ++q.issued; ++q.z; --q.left;
     }
@@ -264,10 +314,18 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   };
   if (tid == 0 || !TMA) issue_upto(S);
 
-  auto acquire = [&](int L) {
+  uint32_t bphase = 0;  // (bulk path) parity of every stage's barrier: only some planes complete a phase
+  // returns the plane's shift code: bit 0 = box row 0 is shifted, bit 1 = the rows alternate
+  auto acquire = [&](int L, int z, int code) -> int {
     const int s = L % S;
+    int sa;
     if (TMA) {
       mbar_wait(&full[s], (uint32_t)(L / S) & 1u);  // load L is the (L / S)-th use of its stage
+      return 0;
+    } else if (BULK && bulk_plane(code, z, sa)) {
+      mbar_wait(&full[s], (bphase >> s) & 1u);
+      bphase ^= 1u << s;
+      return sa | (sb << 1);
     } else {
       // plane L's group must have landed; issued - 1 - L younger groups may still be in flight
       const int younger = rb.issued - 1 - L;
@@ -278,15 +336,53 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       else if (younger == 4) cp_async_wait_group<4>();
       else cp_async_wait_group<5>();
       __syncthreads();  // everybody's share of the plane is visible
+      return 0;
     }
   };
   const int lx = (tid % 32) * V, ly = (tid / 32) * R;
   const int coff = (ly + 1) * BW + V + lx;   // the thread's first cell inside an intermediate plane
   const int scoff = (ly + 1) * SP + V + lx;  // ... inside a staged source box
-  auto centres = [&](T (&dst)[R][V], int L) {
-    const T *sp = reinterpret_cast<const T *>(smem + (L % S) * SSTAGE) + scoff;
+  // (bulk path) the thread's column in box rows ly + j of a staged plane with shift code sc: rows with even j start at
+  // pe + j * SP, rows with odd j at po + j * SP
+  auto row_ptrs = [&](int L, int sc, const T *&pe, const T *&po) {
+    const T *p = reinterpret_cast<const T *>(smem + (L % S) * SSTAGE) + ly * SP + V + lx;
+    const int a = (sc + (sc >> 1) * ly) & 1;
+    pe = p + a;
+    po = p + (a ^ (sc >> 1));
+  };
+  auto centres = [&](T (&dst)[R][V], int L, int sc) {
+    if constexpr (BULK) {
+      const T *pe, *po;
+      row_ptrs(L, sc, pe, po);
 #pragma unroll
-    for (int r = 0; r < R; ++r) lds_v<T>(dst[r], sp + r * SP);
+      for (int r = 0; r < R; ++r) {
+        const T *p = (((r + 1) & 1) ? po : pe) + (r + 1) * SP;
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[r][v] = p[v];
+      }
+    } else {
+      const T *sp = reinterpret_cast<const T *>(smem + (L % S) * SSTAGE) + scoff;
+#pragma unroll
+      for (int r = 0; r < R; ++r) lds_v<T>(dst[r], sp + r * SP);
+    }
+  };
+  // the in-plane neighbours of the thread's cells in a staged source plane
+  auto src_nbrs = [&](int L, int sc, const T (&pc)[R][V], Nbrs<T, R, V> &nb) {
+    if constexpr (BULK) {
+      const T *pe, *po;
+      row_ptrs(L, sc, pe, po);
+      const T *pb2 = (((R + 1) & 1) ? po : pe) + (R + 1) * SP;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { nb.ytop[v] = pe[v]; nb.ybot[v] = pb2[v]; }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T *p = (((r + 1) & 1) ? po : pe) + (r + 1) * SP;
+        nb.xl[r] = p[-1];
+        nb.xr[r] = p[V];
+      }
+    } else {
+      load_nbrs<T, R, V, SP>(reinterpret_cast<const T *>(smem + (L % S) * SSTAGE) + scoff, pc, nb);
+    }
   };
 
   int Lc = 0;
@@ -296,13 +392,14 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     item_geom(it, oz0, nz, oy0, ox0);
     const int yB0 = oy0 - 1, xB0 = ox0 - V;  // origin of the stage-1 tile
     const int cs = oz0 + P.sz2;              // source-frame plane of the first result plane
-    acquire(Lc);
-    acquire(Lc + 1);
+    const int bz = oz0 + P.sz2 - 2, icode = xy_code(oy0 - 2, ox0 - 2 * V);  // the item's first source box
+    const int sc0 = acquire(Lc, bz, icode);
+    int sc_mid = acquire(Lc + 1, bz + 1, icode);  // shift code of the middle source plane of the next step
     // the three source planes and the three intermediate planes a step touches live in registers and
     // rotate by NAME (the loop is unrolled three times), not by copying
     T Z0[R][V], Z1[R][V], Z2[R][V], U0[R][V], U1[R][V], U2[R][V];
-    centres(Z0, Lc);
-    centres(Z1, Lc + 1);
+    centres(Z0, Lc, sc0);
+    centres(Z1, Lc + 1, sc_mid);
     if (DETECT) {  // the two planes below the item's first result plane are nobody's result in this launch
 #pragma unroll
       for (int r = 0; r < R; ++r) { track_row(bad, Z0[r]); track_row(bad, Z1[r]); }
@@ -324,8 +421,8 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
     // the intermediate values then need no masking on planes inside the array
     const bool tile_inside = yB0 >= 0 && yB0 + C::TYB <= P.in_h && xB0 >= 0 && xB0 + C::TXB <= P.in_w;
     const bool whole = P.vec_store && gx + V <= P.in_w;
-    const long long plane = (long long)P.in_h * P.in_w;
-    long long ooff = ((long long)oz0 * P.in_h + (yB0 + ly)) * P.in_w + gx;  // row 0 of result plane oz0 (used where rows says so)
+    const long long plane = (long long)P.in_h * P.pitch;
+    long long ooff = ((long long)oz0 * P.in_h + (yB0 + ly)) * P.pitch + gx;  // row 0 of result plane oz0 (used where rows says so)
 
     // one step: source planes zm (below), zc (middle) in, zp loaded; intermediate planes um, uc in, up produced
     auto step = [&](int k, const T (&zm)[R][V], const T (&zc)[R][V], T (&zp)[R][V], const T (&um)[R][V], const T (&uc)[R][V],
@@ -335,13 +432,14 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       // before the wait for the new plane, so their latency overlaps it
       Nbrs<T, R, V> nb;
 #if MB_TB2_HOIST
-      load_nbrs<T, R, V, SP>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * SSTAGE) + scoff, zc, nb);
+      src_nbrs(Lc + k + 1, sc_mid, zc, nb);
 #endif
-      acquire(Lc + k + 2);
-      centres(zp, Lc + k + 2);
+      const int sc_new = acquire(Lc + k + 2, bz + k + 2, icode);
+      centres(zp, Lc + k + 2, sc_new);
 #if !MB_TB2_HOIST
-      load_nbrs<T, R, V, SP>(reinterpret_cast<const T *>(smem + ((Lc + k + 1) % S) * SSTAGE) + scoff, zc, nb);
+      src_nbrs(Lc + k + 1, sc_mid, zc, nb);
 #endif
+      sc_mid = sc_new;
       if (DETECT == 2 || (DETECT == 1 && k >= nz)) {  // ... nor are the two planes above its last one
 #pragma unroll
         for (int r = 0; r < R; ++r) track_row(bad, zp[r]);
@@ -392,14 +490,14 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
           for (int r = 0; r < R; ++r) {
             uint4 q;
             memcpy(&q, res[r], 16);
-            if ((rows >> r) & 1u) *reinterpret_cast<uint4 *>(dst + (size_t)r * P.in_w) = q;
+            if ((rows >> r) & 1u) *reinterpret_cast<uint4 *>(dst + (size_t)r * P.pitch) = q;
           }
         } else {
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int v = 0; v < V; ++v)
-              if (((rows >> r) & 1u) && gx + v < P.in_w) dst[(size_t)r * P.in_w + v] = res[r][v];
+              if (((rows >> r) & 1u) && gx + v < P.in_w) dst[(size_t)r * P.pitch + v] = res[r][v];
         }
 #else
         T *dst = out + ooff;
@@ -410,11 +508,11 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
             if (whole) {
               uint4 q;
               memcpy(&q, res[r], 16);
-              *reinterpret_cast<uint4 *>(dst + (size_t)r * P.in_w) = q;
+              *reinterpret_cast<uint4 *>(dst + (size_t)r * P.pitch) = q;
             } else {
 #pragma unroll
               for (int v = 0; v < V; ++v)
-                if (gx + v < P.in_w) dst[(size_t)r * P.in_w + v] = res[r][v];
+                if (gx + v < P.in_w) dst[(size_t)r * P.pitch + v] = res[r][v];
             }
           }
         }
@@ -455,17 +553,19 @@ static int launch_tb2_r(Ctx *c, const Plan &p, const void *d_in, void *d_out, co
   if (P.z1 <= P.z0) return MB_OK;
   P.tiles_x = (P.in_w + C::OX - 1) / C::OX;
   P.tiles_y = (P.in_h + C::OY - 1) / C::OY;
-  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.in_w * sizeof(T)) % 16 == 0;
+  P.pitch = c->out_pitch ? (int)c->out_pitch : P.in_w;
+  P.vec_store = ((uintptr_t)d_out % 16 == 0) && ((size_t)P.pitch * sizeof(T)) % 16 == 0;
   Coef27b<T> K;
   std::memcpy(K.k, p.c1.data(), sizeof(T) * 27);
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[3] = {1u, (uint32_t)C::BH, (uint32_t)C::BW};
-  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box)) ? 1 : 0;
+  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 3, d_in, p.in_dims, box, c->in_pitch)) ? 1 : 0;
+  if (c->in_pitch && !P.use_tma) return fail(c, MB_ERR_UNSUPPORTED, "internal: padded arrays need a tensor map");
   auto kern_tma = vol3d_tb2_kernel<T, REV, R_, DETECT, true>;
   auto kern_cp = vol3d_tb2_kernel<T, REV, R_, DETECT, false>;
   auto kern = P.use_tma ? kern_tma : kern_cp;
-  const int smem_bytes = C::SMEM;
+  const int smem_bytes = P.use_tma ? C::SMEM : C::SMEM_NT;
   static int occ_dev[64][2] = {{0}};
   int &occ = occ_dev[c->device & 63][P.use_tma];
   if (occ == 0) {

@@ -212,6 +212,111 @@ static int copy_d2h(Ctx *c, void *dst, const void *src, size_t bytes) {
   return MB_OK;
 }
 
+// One pair of steps with the two-step kernel cur -> nxt.  No promise given (flag): if the kernel met Inf / NaN (in
+// the input or the intermediate array) the pair is redone with the strict kernel.  All redo launches return at once
+// while the flag is clear.  With a spare array of nxt's... (see callers) the redo goes cur -> spare -> nxt; without,
+// cur -> nxt -> cur and a copy to where the result belongs (cur and nxt then share a layout of `bytes` bytes).
+static int tb2_pair(Ctx *c, const DevPlan *dp, int tb2, void *cur, void *nxt, void *spare, int64_t spare_pitch, size_t bytes) {
+  unsigned *flag = tb2 == 2 ? c->d_flag : nullptr;
+  if (flag) MB_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
+  int st = launch_vol3d_tb2(c, dp->p, cur, nxt, nullptr, 0, 0, dp->p.in_dims[0], flag);
+  if (st) return st;  // (-1: the array cannot be described to TMA and has no other staging path: single steps)
+  if (flag) {
+    if (spare) {
+      const int64_t ip = c->in_pitch, op = c->out_pitch;
+      c->out_pitch = spare_pitch;
+      st = launch_vol3d_dense_cond(c, *dp, cur, spare, flag);
+      c->in_pitch = spare_pitch; c->out_pitch = op;
+      if (st == 0) st = launch_vol3d_dense_cond(c, *dp, spare, nxt, flag);
+      c->in_pitch = ip;
+      if (st == -1) return fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo");
+      if (st) return st;
+    } else {
+      if ((st = launch_vol3d_dense_cond(c, *dp, cur, nxt, flag)) == -1) return fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo");
+      if (st) return st;
+      if ((st = launch_vol3d_dense_cond(c, *dp, nxt, cur, flag))) return st;
+      if ((st = launch_cond_copy(c, nxt, cur, bytes, flag))) return st;
+    }
+    c->last_kernel = "vol3d_tb2";
+  }
+  return MB_OK;
+}
+
+// the iteration proper on two arrays of the same layout: dense, or (c->in_pitch = c->out_pitch set by the caller) padded
+static int iterate_core(Ctx *c, const DevPlan *dp, void *a, void *b, int64_t n_steps, void **result) {
+  int st;
+  void *cur = a, *nxt = b;
+  int64_t s = 0;
+  const int tb2 = dp->p.same_shape() ? vol3d_tb2_mode(c, dp->p) : 0;
+  if (tb2 == 2 && ensure_flag(c) != MB_OK) return fail(c, MB_ERR_CUDA, "cannot allocate the check flag");
+  const size_t bytes = c->out_pitch ? (size_t)(dp->p.out_elems / dp->p.out_dims[dp->p.rank - 1]) * (size_t)c->out_pitch * dp->p.esize
+                                    : (size_t)dp->p.out_elems * dp->p.esize;
+  if (tb2) {
+    // temporal blocking: pairs of steps in one pass over HBM; an odd last step runs singly below
+    for (; s + 2 <= n_steps; s += 2) {
+      st = tb2_pair(c, dp, tb2, cur, nxt, nullptr, 0, bytes);
+      if (st == -1) break;
+      if (st) return st;
+      void *t = cur; cur = nxt; nxt = t;
+    }
+  }
+  for (; s < n_steps; ++s) {
+    st = launch_plan(c, *dp, cur, nxt, nullptr);
+    if (st) return st;
+    void *t = cur; cur = nxt; nxt = t;
+  }
+  *result = cur;
+  return MB_OK;
+}
+
+// The same from DENSE a to DENSE b through a padded pair p1, p2 (row pitch `pitch`): the first pass reads the dense
+// array and writes padded rows, the last one reads padded rows and writes b, the passes in between run on the pair.
+static int iterate_through_padded(Ctx *c, const DevPlan *dp, void *a, void *b, void *p1, void *p2, int64_t pitch, int64_t n_steps) {
+  const int tb2 = vol3d_tb2_mode(c, dp->p);
+  if (tb2 == 2 && ensure_flag(c) != MB_OK) return fail(c, MB_ERR_CUDA, "cannot allocate the check flag");
+  const size_t pbytes = (size_t)(dp->p.out_elems / dp->p.out_dims[2]) * (size_t)pitch * dp->p.esize;
+  const int64_t pairs = n_steps / 2, npass = pairs + (n_steps & 1);
+  void *cur = a;
+  int64_t cur_pitch = 0;
+  int st = MB_OK;
+  for (int64_t i = 0; i < npass && st == MB_OK; ++i) {
+    const bool last = i == npass - 1;
+    void *out = last ? b : (cur == p1 ? p2 : p1);
+    const int64_t out_pitch = last ? 0 : pitch;
+    // a padded array that is neither read nor written by this pass (none while both of the pair are in use)
+    void *spare = (cur != p1 && out != p1) ? p1 : ((cur != p2 && out != p2) ? p2 : nullptr);
+    c->in_pitch = cur_pitch; c->out_pitch = out_pitch;
+    if (i < pairs) {
+      st = tb2_pair(c, dp, tb2, cur, out, spare, pitch, pbytes);
+      if (st == -1) st = fail(c, MB_ERR_UNSUPPORTED, "internal: two-step kernel declined a padded pass");
+    } else {
+      st = launch_plan(c, *dp, cur, out, nullptr);
+    }
+    cur = out; cur_pitch = out_pitch;
+  }
+  c->in_pitch = c->out_pitch = 0;
+  return st;
+}
+
+// Rank-3 arrays whose rows are not whole 16-byte units cannot be described to TMA, and the kernels' other staging paths
+// run at two thirds of its speed.  An ITERATION does not have to live in the caller's layout: the two-step
+// kernel's plans (3x3x3 star, Fill 0, same shape) iterate on a pair of arrays whose rows are padded to the next
+// 16-byte multiple — the tensor map describes the logical width, so the pad column is never read or written.
+// Returns the pitch in elements, 0 when the plan iterates where it is.
+static int64_t iterate_pitch(Ctx *c, const DevPlan *dp, int64_t n_steps) {
+  const Plan &p = dp->p;
+  if (c->no_tma || c->force_generic || c->no_pitch || c->prefer_smallwin || p.rank != 3 || !p.same_shape() || !p.post.empty()) return 0;
+  const int64_t w = p.in_dims[2], v = 16 / p.esize;
+  if (p.esize < 4 || w % v == 0 || n_steps < 6 || p.in_elems < c->tile_min_elems) return 0;
+  if (!vol3d_tb2_mode(c, p)) return 0;
+  return (w + v - 1) / v * v;
+}
+
+static int copy_rows(Ctx *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t rows, cudaMemcpyKind kind) {
+  MB_CUDA(c, cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, kind, c->stream));
+  return MB_OK;
+}
+
 static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t *dims, void *a, void *b,
                               int64_t n_steps, void **result) {
   if (n_steps < 1) return fail(c, MB_ERR_INVALID_DESC, "iterateUntil applies the step at least once");
@@ -223,38 +328,23 @@ static int iterate_dev_locked(Ctx *c, const mb_stencil_desc *desc, const int64_t
     st = life_iterate(c, *dp, a, b, n_steps, result);
     if (st != -1) return st;
   }
-  void *cur = a, *nxt = b;
-  int64_t s = 0;
-  const int tb2 = dp->p.same_shape() ? vol3d_tb2_mode(c, dp->p) : 0;
-  if (tb2 == 2 && ensure_flag(c) != MB_OK) return fail(c, MB_ERR_CUDA, "cannot allocate the check flag");
-  if (tb2) {
-    // temporal blocking: pairs of steps in one pass over HBM; an odd last step runs singly below
-    for (; s + 2 <= n_steps; s += 2) {
-      unsigned *flag = tb2 == 2 ? c->d_flag : nullptr;
-      if (flag) MB_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
-      st = launch_vol3d_tb2(c, dp->p, cur, nxt, nullptr, 0, 0, dp->p.in_dims[0], flag);
-      if (st == -1) break;  // the array cannot be described to TMA: single steps
-      if (st) return st;
-      if (flag) {
-        // no promise was given: if the kernel met Inf / NaN (in the input or the intermediate array) the
-        // pair is redone with the strict kernel — cur -> nxt -> cur, then copied to where the result
-        // belongs.  All three launches return immediately while the flag is clear.
-        if ((st = launch_vol3d_dense_cond(c, *dp, cur, nxt, flag)) == -1) return fail(c, MB_ERR_UNSUPPORTED, "internal: strict redo");
-        if (st) return st;
-        if ((st = launch_vol3d_dense_cond(c, *dp, nxt, cur, flag))) return st;
-        if ((st = launch_cond_copy(c, nxt, cur, (size_t)dp->p.out_elems * dp->p.esize, flag))) return st;
-        c->last_kernel = "vol3d_tb2";
-      }
-      void *t = cur; cur = nxt; nxt = t;
+  // the caller's arrays are dense: the first and the last pass change the layout, so the padded pair pays from three
+  // passes on
+  const int64_t pitch = iterate_pitch(c, dp.get(), n_steps);
+  if (pitch) {
+    const Plan &p = dp->p;
+    const size_t pb = (size_t)(p.in_dims[0] * p.in_dims[1]) * (size_t)pitch * p.esize;
+    void *p1 = nullptr, *p2 = nullptr;
+    // (no room for the pair: iterate where the arrays are)
+    if (ensure_scratch(c, 3, pb, &p1) == MB_OK && ensure_scratch(c, 4, pb, &p2) == MB_OK) {
+      if ((st = iterate_through_padded(c, dp.get(), a, b, p1, p2, pitch, n_steps))) return st;
+      *result = b;
+      return MB_OK;
     }
+    cudaGetLastError();
+    c->err.clear();
   }
-  for (; s < n_steps; ++s) {
-    st = launch_plan(c, *dp, cur, nxt, nullptr);
-    if (st) return st;
-    void *t = cur; cur = nxt; nxt = t;
-  }
-  *result = cur;
-  return MB_OK;
+  return iterate_core(c, dp.get(), a, b, n_steps, result);
 }
 
 // iterateUntil with a device-side predicate: chunks of check_every applications; the last application of a chunk is
@@ -535,6 +625,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "tb2") g.c->tb2 = (int)value;
   else if (k == "no_p2p") g.c->no_p2p = (int)value;
   else if (k == "prefer_smallwin") g.c->prefer_smallwin = (int)value;
+  else if (k == "no_pitch") g.c->no_pitch = (int)value;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }
@@ -744,6 +835,27 @@ int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, cons
   for (int i = 0; i < desc->rank; ++i) n *= (size_t)dims[i];
   void *a = nullptr, *b = nullptr, *res = nullptr;
   int st;
+  // the device layout is ours to choose: rows padded to 16-byte units where that lets the iteration use TMA
+  // (iterate_pitch); the copies place and gather the rows
+  if (n_steps >= 1 && n) {
+    std::shared_ptr<DevPlan> dp;
+    if ((st = get_dev_plan(c, desc, dims, &dp))) return st;
+    const int64_t pitch = iterate_pitch(c, dp.get(), n_steps);
+    if (pitch) {
+      const Plan &p = dp->p;
+      const size_t rows = (size_t)(p.in_dims[0] * p.in_dims[1]), rb = (size_t)p.in_dims[2] * p.esize, pb = (size_t)pitch * p.esize;
+      if ((st = ensure_scratch(c, 0, rows * pb, &a))) return st;
+      if ((st = ensure_scratch(c, 1, rows * pb, &b))) return st;
+      if ((st = copy_rows(c, a, pb, host_in, rb, rb, rows, cudaMemcpyHostToDevice))) return st;
+      c->in_pitch = c->out_pitch = pitch;
+      st = iterate_core(c, dp.get(), a, b, n_steps, &res);
+      c->in_pitch = c->out_pitch = 0;
+      if (st) return st;
+      if ((st = copy_rows(c, host_out, rb, res, pb, rb, rows, cudaMemcpyDeviceToHost))) return st;
+      MB_CUDA(c, cudaStreamSynchronize(c->stream));
+      return MB_OK;
+    }
+  }
   if ((st = ensure_scratch(c, 0, n ? n : 1, &a))) return st;
   if ((st = ensure_scratch(c, 1, n ? n : 1, &b))) return st;
   if ((st = copy_h2d(c, a, host_in, n))) return st;

@@ -105,8 +105,12 @@ struct Ctx {
   // grow-only device scratch used by the host->host entry points and two-pass fallbacks
   unsigned *d_flag = nullptr;  // "the optimistic kernel met a non-finite value": set by it, read by the conditional redo
   unsigned long long *d_conv = nullptr;  // convergence verdict of iterate_until (k_converge.cu)
-  void *scratch[3] = {nullptr, nullptr, nullptr};
-  size_t scratch_bytes[3] = {0, 0, 0};
+  void *scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // (3, 4: the pitched pair of mb_iterate_dev)
+  size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+  // Iterating on internally PADDED arrays (mb_api.cu, iterate_pitch): the row pitch in elements of the input / output
+  // array the rank-3 kernels see while set; 0 = that array is dense.  Only vol3d / vol3d_tb2 launches happen meanwhile.
+  int64_t in_pitch = 0, out_pitch = 0;
+  int no_pitch = 0;        // mb_ctx_set_option("no_pitch"): iterations stay in the caller's layout
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
   ShardState *shard = nullptr;

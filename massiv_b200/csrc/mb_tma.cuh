@@ -46,8 +46,9 @@ inline bool tma_dtype(int elem, CUtensorMapDataType *dt) {
 // dims/box are given OUTERMOST FIRST (the library's convention); TMA wants innermost first.
 // Returns false when the array cannot be described (alignment / size limits): the caller then
 // fills tiles with ordinary loads instead.
+// row_pitch (elements, 0 = dense): the distance between rows of the innermost dimension when the array is padded.
 inline bool make_tensor_map(CUtensorMap *m, int elem, int esize, int rank, const void *base, const int64_t *dims,
-                            const uint32_t *box) {
+                            const uint32_t *box, int64_t row_pitch = 0) {
   EncodeTiledFn enc = get_encode_tiled();
   CUtensorMapDataType dt;
   if (!enc || !tma_dtype(elem, &dt)) return false;
@@ -66,7 +67,7 @@ inline bool make_tensor_map(CUtensorMap *m, int elem, int esize, int rank, const
       if (pitch % 16 != 0 || pitch >= ((uint64_t)1 << 40)) return false;
       gstr[i - 1] = pitch;
     }
-    pitch *= (uint64_t)dims[o];
+    pitch *= (uint64_t)((i == 0 && row_pitch > 0) ? row_pitch : dims[o]);
   }
   if (((uint64_t)box[rank - 1] * esize) % 16 != 0) return false;
   // L2 promotion: experiment knob MASSIV_B200_L2PROMO = 0 (none) / 64 / 128 / 256
@@ -126,6 +127,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
+// one contiguous run global -> shared through the bulk-copy engine (UBLKCP): both addresses 16-byte aligned, bytes a
+// multiple of 16, completion counted on the mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // ---- cp.async (LDGSTS): the staging path for arrays TMA cannot describe (row pitch not a multiple of
 // 16 bytes, e.g. an odd number of Floats per row) ----
 // one element (4 or 8 bytes) global -> shared, no register staging; src_bytes = 0 writes zeros instead
@@ -158,12 +166,12 @@ template <typename T> __device__ __forceinline__ int lead_elems(const T *p) {
 // zero_outside: cells outside the array are written as zeros (src-size 0) — what TMA's out-of-range fill does;
 // otherwise the caller guarantees that the box lies inside.  `any` is a valid address for the zero-size copies.
 // The caller commits the group.
-template <typename T, int BH, int BW, int NWARPS>
+template <typename T, int BH, int BW, int NWARPS, int PITCH = BW>
 __device__ __forceinline__ void stage_box(T *dst, const T *plane, const T *any, int H, int W, int y0, int x0, int tid) {
   constexpr int V = 16 / (int)sizeof(T);
   const int lane = tid & 31;
   for (int r = tid >> 5; r < BH; r += NWARPS) {
-    T *drow = dst + r * BW;
+    T *drow = dst + r * PITCH;
     const int gy = y0 + r;
     const bool row_ok = plane != nullptr && gy >= 0 && gy < H;
     if (row_ok && x0 >= 0 && x0 + BW <= W) {

@@ -27,3 +27,5 @@ run life        life_bits        1 X=1                 --workload life --steps 1
 run sobel_closure smallwin       4 X=1                 --workload sobel_closure --steps 4
 run sum9x9_u8   smallwin         4 X=1                 --workload sum9x9_u8 --steps 4
 run avg3d       smallwin         4 X=1                 --workload avg3d --steps 4
+run tb2_odd     vol3d_tb2        2 X=1                 --workload heat3d --grid 1535 1535 1535 --steps 4
+run sobel_odd   tile2d_kernel    4 X=1                 --workload sobel --grid 32767 32767 --steps 4
