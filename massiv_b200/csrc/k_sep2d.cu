@@ -55,7 +55,7 @@ template <typename T, int K, int XOFF> struct S2Cfg {
 };
 
 template <typename T, bool REV, int K, int XOFF, bool TMA>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (!TMA && S2Cfg<T, K, XOFF>::REGSTAGE) ? 3 : 2)
 sep2d_kernel(const __grid_constant__ CUtensorMap tmap, const S2Params P, const SepCoef<T, K> C2,
              const T *__restrict__ in, T *__restrict__ out) {
   using C = S2Cfg<T, K, XOFF>;

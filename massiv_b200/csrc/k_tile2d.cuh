@@ -114,8 +114,13 @@ template <typename T, bool FIN> __device__ __forceinline__ T tap_known(T x, T ac
 // TMA: boxes come through the tensor map; false: the array has none (row pitch not a multiple of 16 bytes)
 // and boxes inside the array are staged with cp.async — a separate instantiation, so that the TMA
 // variant's register allocation is not disturbed (the 7x7 Float kernel sits at the 128-register limit).
+// (register staging holds a box in registers: small kernels are kept at 80 registers so that three CTAs share an SM)
 template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false, bool TMA = true>
-__global__ void __launch_bounds__(256, 2)
+#ifndef MB_T2_MINB8
+#define MB_T2_MINB8 2  // (experiment: minimum CTAs per SM of the small 8-byte kernels)
+#endif
+__global__ void __launch_bounds__(256, (!TMA && T2Cfg<T, OP, REV, KH, KW, XOFF>::REGSTAGE && KH * KW <= 9) ? 3
+                                       : (sizeof(T) == 8 && KH * KW <= 9) ? MB_T2_MINB8 : 2)
 tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const Coef<T, KH * KW> K,
               const T *__restrict__ in, T *__restrict__ out) {
   using C = T2Cfg<T, OP, REV, KH, KW, XOFF>;
