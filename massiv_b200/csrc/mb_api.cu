@@ -626,6 +626,7 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   else if (k == "no_p2p") g.c->no_p2p = (int)value;
   else if (k == "prefer_smallwin") g.c->prefer_smallwin = (int)value;
   else if (k == "no_pitch") g.c->no_pitch = (int)value;
+  else if (k == "wavefront_min_mb") g.c->wavefront_min_bytes = (size_t)value << 20;
   else return fail(g.c, MB_ERR_INVALID_DESC, "unknown option " + k);
   return MB_OK;
 }
@@ -825,6 +826,105 @@ int mb_iterate_dev(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, 
   return iterate_dev_locked(g.c, desc, dims, a, b, n_steps, result);
 }
 
+// Host -> host iteration of the two-step kernel's plans with the copies hidden behind the passes.
+// A pass over planes [lo, hi) reads the previous pass's planes [lo - 2, hi + 2), so after the first Z planes of the
+// input have arrived pass p can already produce the planes below Z - 2 (p + 1): the dependency cone of a stencil.  The
+// input travels up in NB blocks; after block k (planes below Z_k) has landed, EVERY pass runs once, pass p over
+// [Z_(k-1) - 2 (p + 1), Z_k - 2 (p + 1)) — a parallelogram in the (plane, pass) diagram, one launch of about D / NB
+// planes per pass and block, all on the compute stream in that order (which is also a valid order for the two
+// ping-pong arrays: a plane only ever moves up in pass level).  Block k + 1 travels while block k's passes run, and the
+// planes whose last pass is done leave for the host while the later blocks' passes run.  What stays exposed is the
+// first block's upload and the last 2 P + D / NB planes' download.
+// No finite promise: one flag collects the kernels' reports over the whole job; if it is set at the end the job is
+// redone the plain way (upload, checked passes with their strict redo, download).
+// -1: not applicable (the caller runs the plain way).
+static int iterate_wavefront(Ctx *c, const DevPlan *dp, const void *host_in, void *host_out, void *a, void *b, int64_t n_steps,
+                             int64_t pitch) {
+  const Plan &p = dp->p;
+  if (!c->pipeline || c->force_generic || p.rank != 3 || !p.same_shape() || !p.post.empty()) return -1;
+  const int tb2 = vol3d_tb2_mode(c, p);
+  const int64_t D = p.in_dims[0], pairs = n_steps / 2, npass = pairs + (n_steps & 1);
+  const int64_t row_elems = pitch ? pitch : p.in_dims[2];
+  const size_t plane_dev = (size_t)p.in_dims[1] * (size_t)row_elems * p.esize;       // bytes per plane on the device
+  const size_t plane_host = (size_t)p.in_dims[1] * (size_t)p.in_dims[2] * p.esize;  // ... in the caller's arrays
+  if (!tb2 || pairs < 2 || D < 16 || plane_host * (size_t)D < c->wavefront_min_bytes) return -1;
+  if (tb2 == 2 && ensure_flag(c) != MB_OK) return -1;
+  const int NB = 8;
+  if (!c->out_stream && cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return -1; }
+  while ((int)c->pipe_events.size() < 2 * 16) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+    c->pipe_events.push_back(e);
+  }
+  unsigned *flag = tb2 == 2 ? c->d_flag + 16 : nullptr;  // (its own word: single-step launches reset c->d_flag[0])
+  auto bail = [&](int st) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->out_stream);
+    cudaGetLastError();
+    c->in_pitch = c->out_pitch = 0;
+    return st;
+  };
+#define MB_WF(expr)                                        \
+  do {                                                     \
+    int _ps = ::mb::check_cuda(c, (expr), #expr);          \
+    if (_ps) return bail(_ps);                             \
+  } while (0)
+  MB_WF(cudaEventRecord(c->ev_a, c->stream));  // whatever the caller queued on the compute stream comes first
+  MB_WF(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  MB_WF(cudaStreamWaitEvent(c->out_stream, c->ev_a, 0));
+  if (flag) MB_WF(cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
+  const size_t rb = (size_t)p.in_dims[2] * p.esize, pb = (size_t)row_elems * p.esize;
+  auto Z = [&](int k) { return D * (k + 1) / NB; };  // planes [0, Z(k)) have arrived after block k
+  // uploads, in order, on the copy stream
+  for (int k = 0; k < NB; ++k) {
+    const int64_t z0 = k ? Z(k - 1) : 0, z1 = Z(k);
+    const char *src = (const char *)host_in + (size_t)z0 * plane_host;
+    char *dst = (char *)a + (size_t)z0 * plane_dev;
+    if (pitch) MB_WF(cudaMemcpy2DAsync(dst, pb, src, rb, rb, (size_t)(z1 - z0) * (size_t)p.in_dims[1], cudaMemcpyHostToDevice, c->comm_stream));
+    else MB_WF(cudaMemcpyAsync(dst, src, (size_t)(z1 - z0) * plane_host, cudaMemcpyHostToDevice, c->comm_stream));
+    MB_WF(cudaEventRecord(c->pipe_events[k], c->comm_stream));
+  }
+  void *fin = (npass & 1) ? b : a;  // where the last pass writes
+  c->in_pitch = c->out_pitch = pitch;
+  int64_t sent = 0;  // planes [0, sent) of the result are on their way to the host
+  for (int k = 0; k < NB; ++k) {
+    MB_WF(cudaStreamWaitEvent(c->stream, c->pipe_events[k], 0));
+    for (int64_t q = 0; q < npass; ++q) {
+      const int64_t back = 2 * (q + 1);
+      OuterRange r;
+      r.o0 = k == 0 ? 0 : std::max<int64_t>(0, Z(k - 1) - back);
+      r.o1 = k == NB - 1 ? D : std::max<int64_t>(0, Z(k) - back);
+      if (r.o1 <= r.o0) continue;
+      void *in = (q & 1) ? b : a, *out = (q & 1) ? a : b;
+      int st = q < pairs ? launch_vol3d_tb2(c, p, in, out, &r, 0, 0, D, flag) : launch_plan(c, *dp, in, out, &r);
+      if (st == -1) st = fail(c, MB_ERR_UNSUPPORTED, "internal: two-step kernel declined a block of the wavefront");
+      if (st) return bail(st);
+    }
+    // the planes whose last pass is done leave while the next blocks' passes run
+    const int64_t done = k == NB - 1 ? D : std::max<int64_t>(0, Z(k) - 2 * npass);
+    if (done > sent) {
+      MB_WF(cudaEventRecord(c->pipe_events[16 + k], c->stream));
+      MB_WF(cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
+      char *dst = (char *)host_out + (size_t)sent * plane_host;
+      const char *src = (const char *)fin + (size_t)sent * plane_dev;
+      if (pitch) MB_WF(cudaMemcpy2DAsync(dst, rb, src, pb, rb, (size_t)(done - sent) * (size_t)p.in_dims[1], cudaMemcpyDeviceToHost, c->out_stream));
+      else MB_WF(cudaMemcpyAsync(dst, src, (size_t)(done - sent) * plane_host, cudaMemcpyDeviceToHost, c->out_stream));
+      sent = done;
+    }
+  }
+  c->in_pitch = c->out_pitch = 0;
+  c->last_kernel = "vol3d_tb2";
+  // join: later work on the compute stream (and the caller) sees everything done
+  MB_WF(cudaEventRecord(c->ev_b, c->out_stream));
+  MB_WF(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  unsigned seen = 0;
+  if (flag) MB_WF(cudaMemcpyAsync(&seen, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  MB_WF(cudaStreamSynchronize(c->stream));
+#undef MB_WF
+  return seen ? -2 : MB_OK;  // -2: Inf / NaN met on the way — redo strictly
+}
+
 int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in, void *host_out,
                int64_t n_steps) {
   Guard g(h);
@@ -846,6 +946,7 @@ int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, cons
       const size_t rows = (size_t)(p.in_dims[0] * p.in_dims[1]), rb = (size_t)p.in_dims[2] * p.esize, pb = (size_t)pitch * p.esize;
       if ((st = ensure_scratch(c, 0, rows * pb, &a))) return st;
       if ((st = ensure_scratch(c, 1, rows * pb, &b))) return st;
+      if ((st = iterate_wavefront(c, dp.get(), host_in, host_out, a, b, n_steps, pitch)) >= 0) return st;
       if ((st = copy_rows(c, a, pb, host_in, rb, rb, rows, cudaMemcpyHostToDevice))) return st;
       c->in_pitch = c->out_pitch = pitch;
       st = iterate_core(c, dp.get(), a, b, n_steps, &res);
@@ -858,6 +959,11 @@ int mb_iterate(mb_ctx *h, const mb_stencil_desc *desc, const int64_t *dims, cons
   }
   if ((st = ensure_scratch(c, 0, n ? n : 1, &a))) return st;
   if ((st = ensure_scratch(c, 1, n ? n : 1, &b))) return st;
+  if (n_steps >= 1 && n) {
+    std::shared_ptr<DevPlan> dp;
+    if ((st = get_dev_plan(c, desc, dims, &dp))) return st;
+    if (dp->p.same_shape() && (st = iterate_wavefront(c, dp.get(), host_in, host_out, a, b, n_steps, 0)) >= 0) return st;
+  }
   if ((st = copy_h2d(c, a, host_in, n))) return st;
   if ((st = iterate_dev_locked(c, desc, dims, a, b, n_steps, &res))) return st;
   if ((st = copy_d2h(c, host_out, res, n))) return st;

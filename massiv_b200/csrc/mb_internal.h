@@ -110,6 +110,7 @@ struct Ctx {
   // Iterating on internally PADDED arrays (mb_api.cu, iterate_pitch): the row pitch in elements of the input / output
   // array the rank-3 kernels see while set; 0 = that array is dense.  Only vol3d / vol3d_tb2 launches happen meanwhile.
   int64_t in_pitch = 0, out_pitch = 0;
+  size_t wavefront_min_bytes = (size_t)256 << 20;  // mb_iterate hides its copies behind the passes from this size on ("wavefront_min_mb")
   int no_pitch = 0;        // mb_ctx_set_option("no_pitch"): iterations stay in the caller's layout
   void *pinned = nullptr;
   size_t pinned_bytes = 0;

@@ -67,3 +67,43 @@ def test_separable_two_pass_host_to_host(border):
         assert bits_equal(M.computeSeparable(border_obj(border, 0.25), row, col, img), want)
     finally:
         dev.set_option("pipeline", 1)
+
+
+@pytest.mark.parametrize("dtname", ["float64", "float32"])
+def test_iterate_host_to_host_wavefront(dtname):
+    """mb_iterate on the two-step kernel's plans sends the input up in blocks and runs every pass on the part of the
+    array whose dependency cone has arrived (mb_api.cu: iterate_wavefront); the result must be that of stepping the
+    oracle — even and odd step counts, rows TMA cannot describe (padded on the device), and Inf / NaN in the input
+    (the job is then redone strictly)."""
+    dev = M.Device.default()
+    dt = np.dtype(dtname)
+    rng = np.random.default_rng(21)
+    k = np.zeros((3, 3, 3), dt)
+    for ix in ((1, 1, 1), (0, 1, 1), (2, 1, 1), (1, 0, 1), (1, 2, 1), (1, 1, 0), (1, 1, 2)):
+        k[ix] = rng.standard_normal() * 0.3
+    co = k.reshape(-1).tolist()
+    st = M.makeCorrelationStencilFromKernel(k)
+    dev.set_option("wavefront_min_mb", 0)
+    dev.set_option("tile_min_elems", 0)
+    try:
+        for shape in ((40, 70, 136), (67, 50, 131), (16, 40, 64)):
+            arr = rng.standard_normal(shape).astype(dt)
+            bad = arr.copy()
+            bad[shape[0] - 3, 5, 7] = np.inf
+            for n in (4, 7, 12, 30):
+                want = O.iterate("corr", arr, n, size=(3, 3, 3), coeffs=co, border="fill", fill=0.0, nthreads=16)
+                assert bits_equal(M.iterateStencil(n, M.Fill(0.0), st, arr), want), (shape, n)
+                assert dev.last_kernel in ("vol3d_tb2", "vol3d_star7")
+            want = O.iterate("corr", bad, 7, size=(3, 3, 3), coeffs=co, border="fill", fill=0.0, nthreads=16)
+            assert bits_equal(M.iterateStencil(7, M.Fill(0.0), st, bad), want), (shape, "inf")
+            # and with the caller's promise (no flag, no redo)
+            want = O.iterate("corr", arr, 6, size=(3, 3, 3), coeffs=co, border="fill", fill=0.0, nthreads=16)
+            assert bits_equal(M.iterateStencil(6, M.Fill(0.0), st.assumeFinite(), arr), want), (shape, "promise")
+        dev.set_option("pipeline", 0)
+        arr = rng.standard_normal((40, 70, 136)).astype(dt)
+        want = O.iterate("corr", arr, 5, size=(3, 3, 3), coeffs=co, border="fill", fill=0.0, nthreads=16)
+        assert bits_equal(M.iterateStencil(5, M.Fill(0.0), st, arr), want)
+    finally:
+        dev.set_option("pipeline", 1)
+        dev.set_option("wavefront_min_mb", 256)
+        dev.set_option("tile_min_elems", 16384)
