@@ -214,8 +214,12 @@ int mb_sync(mb_ctx *ctx);
  * "life_bitpack" (0 = byte-wise Life kernels only), "tile_min_elems" (arrays below this many output
  * cells take the generic kernel), "no_tma" (stage tiles with cp.async), "no_known" (no compile-time
  * coefficient kernels), "tb2" (0 = one step per pass when iterating), "no_optimistic" (1 = never skip
- * zero taps without the caller's promise), "pipeline" (0 = serial copies in mb_run), "no_p2p" (1 = sharded
- * iteration moves halo planes with ncclSend/ncclRecv; must be set alike on every rank) */
+ * zero taps without the caller's promise), "pipeline" (0 = serial copies in mb_run / mb_run_sep2 / mb_iterate),
+ * "no_p2p" (1 = sharded iteration moves halo planes with ncclSend/ncclRecv; must be set alike on every rank),
+ * "prefer_smallwin" (1 = the table-driven small-window kernel before the compile-time-shaped ones), "no_pitch"
+ * (1 = iterations over rank-3 arrays without a tensor map stay in the caller's layout instead of running on an
+ * internal pair with padded rows), "wavefront_min_mb" (mb_iterate hides its copies behind the passes for arrays
+ * of at least this many MiB; default 256) */
 int mb_ctx_set_option(mb_ctx *ctx, const char *key, int64_t value);
 /* number of kernels of THIS library launched through the context so far */
 int64_t mb_launch_count(mb_ctx *ctx);
@@ -261,7 +265,9 @@ int mb_run_sep2(mb_ctx *ctx, const mb_stencil_desc *first, const mb_stencil_desc
 
 /* iterateUntil (\n _ _ -> n >= n_steps-1) (\_ -> applyStencil ...)  (Manifest/Internal.hs:331-397):
  * the stencil is applied n_steps (>= 1) times, double-buffered; output size must equal input size.
- * dev_a holds the input; *result receives dev_a or dev_b, whichever holds the last array. */
+ * dev_a holds the input; *result receives dev_a or dev_b, whichever holds the last array; BOTH arrays are
+ * overwritten.  The host -> host form overlaps its copies with the passes where the stencil allows (the 3x3x3
+ * star under Fill 0: a pass runs inside the dependency cone of what has arrived). */
 int mb_iterate_dev(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, void *dev_a,
                    void *dev_b, int64_t n_steps, void **result);
 int mb_iterate(mb_ctx *ctx, const mb_stencil_desc *desc, const int64_t *dims, const void *host_in,
