@@ -56,7 +56,10 @@ template <typename T, int OP, bool REV, int KH, int KW, int XOFF> struct T2Cfg {
   static constexpr int WX = sizeof(T) == 8 ? MB_T2_WX64 : 1;
   static constexpr int TX = 32 * WX, TY = 8 / WX;
   static constexpr int TW = TX * V;
-  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : (sizeof(T) == 8 ? MB_T2_R64 : 4);
+#ifndef MB_T2_R32
+#define MB_T2_R32 4
+#endif
+  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : (sizeof(T) == 8 ? MB_T2_R64 : (KH <= 3 ? MB_T2_R32 : 4));
   static constexpr int TH = TY * R;
   static constexpr int HALO = ((XOFF + KW - 1 + V - 1) / V) * V; // halo rounded to whole vectors
   static constexpr int NV = 1 + HALO / V;
