@@ -254,18 +254,21 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
   }
   // May the box of plane z at (y, x) come through the bulk-copy engine?  It must lie inside the array, and not end with
   // the array's last row (a shifted row reads one element past its end).  The in-plane part of the answer and the
-  // parity of the box's first element are taken once per item (xy_code: -1 no, else the parity of plane 0's box);
+  // parity of the box's first element are taken once per item (xy_code: -1 no, else bit 0 = the parity of plane 0's
+  // box, bit 1 = the box ends with the plane's last row, bit 2 = it starts with the plane's first element);
   // row r of plane z's box is shifted when (parity + z * (H * W & 1) + r * (W & 1)) is odd.
   const unsigned base_el = (unsigned)(reinterpret_cast<uintptr_t>(in) / sizeof(T));
   const int hw1 = (P.in_h & P.in_w) & 1, sb = P.in_w & 1;
   auto xy_code = [&](int y, int x) -> int {
     if (!BULK || y < 0 || y + C::BH > P.in_h || x < 0 || x + C::BW > P.in_w) return -1;
-    return (int)((base_el + (unsigned)y * (unsigned)P.in_w + (unsigned)x) & 1u) | (y + C::BH == P.in_h ? 2 : 0);
+    return (int)((base_el + (unsigned)y * (unsigned)P.in_w + (unsigned)x) & 1u) | (y + C::BH == P.in_h ? 2 : 0) | ((y | x) == 0 ? 4 : 0);
   };
   auto bulk_plane = [&](int code, int z, int &sa) -> bool {
     sa = 0;
     if (!BULK || code < 0 || z < 0 || z >= P.in_d || ((code & 2) && z == P.in_d - 1)) return false;
-    sa = (code + (z & hw1)) & 1;
+    const int a = (code + (z & hw1)) & 1;
+    if (a && (code & 4) && z == 0) return false;  // (a shifted first row would read the element before the array)
+    sa = a;
     return true;
   };
   auto issue_upto = [&](int limit) {  // limit = planes released so far + S
