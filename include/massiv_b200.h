@@ -210,6 +210,10 @@ const char *mb_last_error(mb_ctx *ctx);
 /* launch the context's kernels on an external cudaStream_t (NULL restores its own stream) */
 int mb_ctx_set_stream(mb_ctx *ctx, void *cuda_stream);
 int mb_sync(mb_ctx *ctx);
+/* Returns the context's grow-only device scratch to the driver (the staging arrays of the host -> host entry points, the
+ * padded pair of an iteration over an array TMA cannot describe — up to four arrays of the largest size seen).  Waits
+ * for the context's streams first.  The next call that needs scratch allocates it again. */
+int mb_ctx_trim(mb_ctx *ctx);
 /* tuning / test switches (none changes a result): "force_generic" (1 = always the generic kernel),
  * "life_bitpack" (0 = byte-wise Life kernels only), "tile_min_elems" (arrays below this many output
  * cells take the generic kernel), "no_tma" (stage tiles with cp.async), "no_known" (no compile-time

@@ -631,6 +631,21 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   return MB_OK;
 }
 
+int mb_ctx_trim(mb_ctx *h) {
+  Guard g(h);
+  if (g.st) return g.st;
+  Ctx *c = g.c;
+  MB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->comm_stream) MB_CUDA(c, cudaStreamSynchronize(c->comm_stream));
+  if (c->out_stream) MB_CUDA(c, cudaStreamSynchronize(c->out_stream));
+  for (int i = 0; i < (int)(sizeof(c->scratch) / sizeof(c->scratch[0])); ++i) {
+    if (c->scratch[i]) MB_CUDA(c, cudaFree(c->scratch[i]));
+    c->scratch[i] = nullptr;
+    c->scratch_bytes[i] = 0;
+  }
+  return MB_OK;
+}
+
 int mb_sync(mb_ctx *h) {
   Guard g(h);
   if (g.st) return g.st;

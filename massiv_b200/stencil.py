@@ -510,6 +510,10 @@ class Device:
     def sync(self):
         self.check(self._L.mb_sync(self._h))
 
+    def trim(self):
+        """give the context's device scratch (staging arrays, padded pairs) back to the driver"""
+        self.check(self._L.mb_ctx_trim(self._h))
+
     def set_option(self, key: str, value: int):
         self.check(self._L.mb_ctx_set_option(self._h, key.encode(), int(value)))
 
