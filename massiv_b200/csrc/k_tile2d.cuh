@@ -44,22 +44,28 @@ template <typename T, int N> struct Coef {
 // XOFF: TMA needs the first byte of every box row 16-byte aligned in global memory, so the box starts
 // at the source column rounded DOWN to a whole vector and the window begins XOFF (< V) elements into
 // the staged row.  XOFF is a template parameter so that the register window is indexed statically.
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF> struct T2Cfg {
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, bool TMA = true> struct T2Cfg {
   static constexpr int V = 16 / (int)sizeof(T);
 #ifndef MB_T2_WX64
-#define MB_T2_WX64 1
+#define MB_T2_WX64 2
 #endif
 #ifndef MB_T2_R64
-#define MB_T2_R64 4
+#define MB_T2_R64 3
 #endif
-  // warps side by side: wider tiles mean longer contiguous DRAM bursts per box row
-  static constexpr int WX = sizeof(T) == 8 ? MB_T2_WX64 : 1;
-  static constexpr int TX = 32 * WX, TY = 8 / WX;
-  static constexpr int TW = TX * V;
 #ifndef MB_T2_R32
 #define MB_T2_R32 4
 #endif
-  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : (sizeof(T) == 8 ? MB_T2_R64 : (KH <= 3 ? MB_T2_R32 : 4));
+  // Double kernels with windows up to three rows are DRAM-bound: two warps side by side make the box rows 1 KiB long
+  // (longer contiguous DRAM bursts) and three rows per thread keep the tile at 128 x 12 cells.  Measured at 16384^2
+  // (scripts/probe_tile2d.py; 1 warp x 4 rows -> 2 x 4 -> 2 x 3): avg3x3 335 -> 346 -> 348 Gcells/s, conv3x3 Reflect
+  // 314 -> 341 -> 364, conv3x3 Fill 0 328 -> 346 -> 386; the 5x5 / 7x7 kernels (two rows per thread) and the Int64
+  // folds lose 3-10 % and keep the one-warp rows.
+  static constexpr bool WIDE = sizeof(T) == 8 && KH <= 3 && std::is_floating_point<T>::value;
+  static constexpr int WX = WIDE ? MB_T2_WX64 : 1;
+  static constexpr int TX = 32 * WX, TY = 8 / WX;
+  static constexpr int TW = TX * V;
+  // (without a tensor map the cp.async-staged wide tile does better with four rows: avg3x3 16383^2 286 against 274)
+  static constexpr int R = (KH >= 5 && sizeof(T) == 8) ? 2 : (WIDE ? (TMA ? MB_T2_R64 : 4) : (sizeof(T) == 4 && KH <= 3 ? MB_T2_R32 : 4));
   static constexpr int TH = TY * R;
   static constexpr int HALO = ((XOFF + KW - 1 + V - 1) / V) * V; // halo rounded to whole vectors
   static constexpr int NV = 1 + HALO / V;
@@ -122,11 +128,11 @@ template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = 
 #ifndef MB_T2_MINB8
 #define MB_T2_MINB8 2  // (experiment: minimum CTAs per SM of the small 8-byte kernels)
 #endif
-__global__ void __launch_bounds__(256, (!TMA && T2Cfg<T, OP, REV, KH, KW, XOFF>::REGSTAGE && KH * KW <= 9) ? 3
+__global__ void __launch_bounds__(256, (!TMA && T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>::REGSTAGE && KH * KW <= 9) ? 3
                                        : (sizeof(T) == 8 && KH * KW <= 9) ? MB_T2_MINB8 : 2)
 tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const Coef<T, KH * KW> K,
               const T *__restrict__ in, T *__restrict__ out) {
-  using C = T2Cfg<T, OP, REV, KH, KW, XOFF>;
+  using C = T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>;
   using A = Arith<T>;
   using Acc = typename A::Acc;
   constexpr int V = C::V, R = C::R, NVV = C::NV * V;
@@ -346,9 +352,10 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
 
 // ---- host side ------------------------------------------------------------------------------------
 
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false>
-static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
-  using C = T2Cfg<T, OP, REV, KH, KW, XOFF>;
+// one launch with the tile geometry of the TMA (tmap != nullptr) or the non-TMA instantiation
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC, bool FIN, bool TMA>
+static int launch_cfg(Ctx *c, const DevPlan &dp, const CUtensorMap &tmap, const void *d_in, void *d_out, const OuterRange *range) {
+  using C = T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>;
   const Plan &p = dp.p;
   T2Params P;
   std::memset(&P, 0, sizeof(P));
@@ -375,16 +382,11 @@ static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
   std::memset(&K, 0, sizeof(K));
   if (!p.c1.empty()) std::memcpy(K.c1, p.c1.data(), sizeof(T) * KH * KW);
   if (!p.c2.empty()) std::memcpy(K.c2, p.c2.data(), sizeof(T) * KH * KW);
-  CUtensorMap tmap;
-  std::memset(&tmap, 0, sizeof(tmap));
-  const uint32_t box[2] = {(uint32_t)C::BH, (uint32_t)C::BW};
-  P.use_tma = (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box)) ? 1 : 0;
-  auto kern_tma = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN, true>;
-  auto kern_cp = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN, false>;
-  auto kern = P.use_tma ? kern_tma : kern_cp;
-  static int occ_dev[64][2] = {{0}};  // per device: the smem opt-in is a per-device function attribute
-  int &occ = occ_dev[c->device & 63][P.use_tma];
-  const int smem_bytes = (!P.use_tma && C::REGSTAGE) ? C::SMEM_RS : C::SMEM;
+  P.use_tma = TMA ? 1 : 0;
+  auto kern = tile2d_kernel<T, OP, REV, KH, KW, XOFF, KC, FIN, TMA>;
+  static int occ_dev[64] = {0};  // per device: the smem opt-in is a per-device function attribute
+  int &occ = occ_dev[c->device & 63];
+  const int smem_bytes = (!TMA && C::REGSTAGE) ? C::SMEM_RS : C::SMEM;
   if (occ == 0) {
     MB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     MB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
@@ -396,6 +398,18 @@ static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, co
   c->launches++;
   c->last_kernel = std::is_void<KC>::value ? "tile2d" : "tile2d_known";
   return check_cuda(c, cudaGetLastError(), "tile2d_kernel launch");
+}
+
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false>
+static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+  using CT = T2Cfg<T, OP, REV, KH, KW, XOFF, true>;
+  const Plan &p = dp.p;
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  const uint32_t box[2] = {(uint32_t)CT::BH, (uint32_t)CT::BW};
+  if (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box))
+    return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, true>(c, dp, tmap, d_in, d_out, range);
+  return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, false>(c, dp, tmap, d_in, d_out, range);
 }
 
 // well-known 3x3 kernels with compile-time coefficients (k_tile2d_known.cu); -1 when none matches
