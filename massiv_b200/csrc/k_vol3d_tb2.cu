@@ -55,7 +55,11 @@ template <typename T, int R_> struct TB2Cfg {
   static constexpr int V = 16 / (int)sizeof(T);
   static constexpr int R = R_;
   static constexpr int NT = 32 * MB_TB2_NW;            // threads per CTA
-  static constexpr int TXB = 32 * V, TYB = MB_TB2_NW * R;  // stage-1 tile
+#ifndef MB_TB2_WX
+#define MB_TB2_WX 1  // warps side by side in x (experiment: longer box rows)
+#endif
+  static constexpr int WX = sizeof(T) == 8 ? MB_TB2_WX : 1;  // (a Float box twice as wide would exceed TMA's 256-element box)
+  static constexpr int TXB = 32 * WX * V, TYB = (MB_TB2_NW / WX) * R;  // stage-1 tile
   static constexpr int OX = TXB - 2 * V, OY = TYB - 2;  // result tile
   static constexpr int BW = TXB + 2 * V, BH = TYB + 2;  // staged box (one-cell halo, vector-padded in x)
   static constexpr int STAGE = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
@@ -342,7 +346,7 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       return 0;
     }
   };
-  const int lx = (tid % 32) * V, ly = (tid / 32) * R;
+  const int lx = (tid % (32 * C::WX)) * V, ly = (tid / (32 * C::WX)) * R;
   const int coff = (ly + 1) * BW + V + lx;   // the thread's first cell inside an intermediate plane
   const int scoff = (ly + 1) * SP + V + lx;  // ... inside a staged source box
   // (bulk path) the thread's column in box rows ly + j of a staged plane with shift code sc: rows with even j start at
