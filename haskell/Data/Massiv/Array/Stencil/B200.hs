@@ -30,6 +30,7 @@ module Data.Massiv.Array.Stencil.B200
   ( -- * Device
     DeviceB200
   , withDeviceB200
+  , trimDeviceB200
     -- * Reified stencils (same names as Data.Massiv.Array.Stencil)
   , StencilB200
   , idStencil
@@ -97,6 +98,8 @@ data MbDesc
 
 foreign import ccall safe "mb_ctx_create"  c_mb_ctx_create  :: CInt -> Ptr (Ptr MbCtx) -> IO CInt
 foreign import ccall safe "mb_ctx_destroy" c_mb_ctx_destroy :: Ptr MbCtx -> IO CInt
+-- | gives the context's device scratch (staging arrays, padded iteration pairs) back to the driver
+foreign import ccall safe "mb_ctx_trim"    c_mb_ctx_trim    :: Ptr MbCtx -> IO CInt
 foreign import ccall safe "mb_last_error"  c_mb_last_error  :: Ptr MbCtx -> IO CString
 foreign import ccall safe "mb_out_dims"    c_mb_out_dims    :: Ptr MbDesc -> Ptr Int64 -> Ptr Int64 -> IO CInt
 foreign import ccall safe "mb_run"         c_mb_run
@@ -138,6 +141,13 @@ withDeviceB200 ordinal = bracket open close
       when (st /= 0) $ throwIO (B200Error (fromIntegral st) "mb_ctx_create: no usable CUDA device (no CPU fallback)")
       DeviceB200 <$> peek pp
     close (DeviceB200 p) = () <$ c_mb_ctx_destroy p
+
+-- | Returns the context's grow-only device scratch (staging arrays of the host-to-host calls, the padded pair of an
+-- iteration over a volume TMA cannot describe) to the driver.
+trimDeviceB200 :: DeviceB200 -> IO ()
+trimDeviceB200 (DeviceB200 p) = do
+  st <- c_mb_ctx_trim p
+  when (st /= 0) $ throwIO (B200Error (fromIntegral st) "mb_ctx_trim")
 
 -- | @mb_kind@
 data Kind = KId | KSum | KProduct | KAvg | KMax | KMin | KConv | KCorr | KTaps | KLife | KMag2
