@@ -910,7 +910,7 @@ def gpu_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20; the step counts of CONFIG_RUNS for the other workloads, e.g. 1000 generations of Life)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("MASSIV_B200_WORKLOAD", "heat3d"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -922,6 +922,10 @@ def main():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
+    if args.steps is None:
+        # heat3d (the driver's workload): 20; the others: what their record in the default run uses (Life only reaches its
+        # on-chip path on long runs: 1000 generations as BASELINE.json's config says)
+        args.steps = dict(CONFIG_RUNS).get(args.workload, 20) if args.impl != "reference" else 20
     if args.impl == "reference":
         reference_main(args)
     else:
