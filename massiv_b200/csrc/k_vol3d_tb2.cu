@@ -103,6 +103,12 @@ template <typename T, int R, int V> struct Nbrs {
 #ifndef MB_TB2_TRACKALL
 #define MB_TB2_TRACKALL 1    // 1: the finite check inspects every result (rim included), stores are predicated, no per-row branches
 #endif
+#ifndef MB_TB2_L2HINT
+#define MB_TB2_L2HINT 0  // 1 / 2: source boxes are fetched with an L2 evict_last / evict_first hint (the rims are read again by the neighbour tiles)
+#endif
+#ifndef MB_TB2_STCS
+#define MB_TB2_STCS 0    // 1: results leave with streaming stores (st.global.cs: first to be evicted from L2)
+#endif
 #ifndef MB_TB2_HOIST
 #define MB_TB2_HOIST 0  // 1: the in-plane neighbour loads of stage 1 are issued before the wait for the new source plane
 #endif
@@ -288,7 +294,11 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
       const int s = q.issued % S;
       if (TMA) {
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::BW * C::BH * sizeof(T)));
+#if MB_TB2_L2HINT
+        tma_load_3d_hint(smem + s * SSTAGE, &tmap, &full[s], q.x, q.y, q.z, l2_policy(MB_TB2_L2HINT));
+#else
         tma_load_3d(smem + s * SSTAGE, &tmap, &full[s], q.x, q.y, q.z);
+#endif
       } else {
         int sa;
         if (BULK && bulk_plane(q.code, q.z, sa)) {
@@ -497,7 +507,11 @@ vol3d_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const TB2Params P, co
           for (int r = 0; r < R; ++r) {
             uint4 q;
             memcpy(&q, res[r], 16);
+#if MB_TB2_STCS
+            if ((rows >> r) & 1u) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)r * P.pitch), q);
+#else
             if ((rows >> r) & 1u) *reinterpret_cast<uint4 *>(dst + (size_t)r * P.pitch) = q;
+#endif
           }
         } else {
 #pragma unroll
