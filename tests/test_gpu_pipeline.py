@@ -107,3 +107,19 @@ def test_iterate_host_to_host_wavefront(dtname):
         dev.set_option("pipeline", 1)
         dev.set_option("wavefront_min_mb", 256)
         dev.set_option("tile_min_elems", 16384)
+
+
+def test_trim_returns_the_scratch_and_the_next_call_allocates_again():
+    import torch
+    dev = M.Device.default()
+    rng = np.random.default_rng(31)
+    arr = rng.standard_normal((3000, 3001))
+    st = M.sumStencil(M.Sz(3, 3))
+    want = O.apply("sum", arr, size=(3, 3), border="edge", nthreads=16)
+    assert bits_equal(M.compute(M.mapStencil(M.Edge, st, arr)), want)   # host -> host: staging arrays in the context
+    torch.cuda.synchronize()
+    before = torch.cuda.mem_get_info()[0]
+    dev.trim()
+    after = torch.cuda.mem_get_info()[0]
+    assert after - before >= 2 * arr.nbytes - (64 << 20), (before, after)
+    assert bits_equal(M.compute(M.mapStencil(M.Edge, st, arr)), want)
