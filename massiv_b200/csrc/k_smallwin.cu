@@ -48,6 +48,9 @@ struct SWParams {
   int stage_bytes;
   int ntaps;             // all terms together
   int bool_canon, skip_zero, trivial;  // trivial: one term, no program beyond it
+  // dense (rank 2, trivial plans): the taps are a full kh x kw window walked row-major (1) or in reverse (2): a loaded
+  // element then serves all the thread's output rows it belongs to, in the order each of them needs it
+  int dense, kh, kw;
   unsigned long long fill_bits;
   const int32_t *taps;   // ntaps x 2 offsets relative to the evaluated index (the plan's table)
   const void *coef;      // ntaps coefficients (zeros where a term has none)
@@ -144,6 +147,77 @@ __device__ __forceinline__ void sw_term_rows(int kind, int nt, int avg_n, const 
   }
   SW_EACH(out[r][c] = A::store(acc[r][c]))
 #undef SW_EACH
+}
+
+// A dense kh x kw window over the thread's 4 rows x 4 columns (32 apart): box rows are visited once, in the order the
+// window is walked (top-down, or bottom-up for a reversed walk); the element of box row y and window column tx is the
+// tap (y - r, tx) of output row r for every r with 0 <= y - r < kh.  Every output still accumulates its taps in the
+// reference's order (row-major over the window, or its reverse), so the bits are those of the tap-list form; one
+// shared-memory load now feeds up to four accumulations.
+template <typename T, bool canon>
+__device__ __forceinline__ void sw_dense(int kind, int kh, int kw, bool reversed, int avg_n, const T *__restrict__ s_k,
+                                         const T *__restrict__ base, int pitch, bool skip_zero, T (&out)[SW_RY][SW_CX]) {
+  using A = Arith<T>;
+  using Acc = typename A::Acc;
+  Acc acc[SW_RY][SW_CX];
+  T m[SW_RY][SW_CX];
+  const bool lin = kind == MB_CONV || kind == MB_CORR || kind == MB_TAPS;
+  const bool mx = kind == MB_MAX;
+#define SW_ALL(BODY)                          \
+  _Pragma("unroll") for (int r = 0; r < SW_RY; ++r) _Pragma("unroll") for (int c = 0; c < SW_CX; ++c) { BODY; }
+  SW_ALL(acc[r][c] = A::from_count(kind == MB_PRODUCT ? 1 : 0))
+  SW_ALL(m[r][c] = mx ? (canon ? T(0) : Bounds<T>::lo()) : (canon ? T(1) : Bounds<T>::hi()))
+  const int nrows = kh + SW_RY - 1;
+  // (measured and rejected: a separate test-free loop for the box rows that lie inside all four windows — sum 9x9
+  // Word8 / Float / Double 93 / 103 / 98 Gcells/s against 108 / 136 / 109 for this form)
+#pragma unroll 1
+  for (int i = 0; i < nrows; ++i) {
+    const int y = reversed ? nrows - 1 - i : i;
+    const T *rowp = base + y * pitch;
+#pragma unroll 1
+    for (int j = 0; j < kw; ++j) {
+      const int tx = reversed ? kw - 1 - j : j;
+      T x[SW_CX];
+#pragma unroll
+      for (int c = 0; c < SW_CX; ++c) {
+        T v = rowp[tx + 32 * c];
+        if (canon) v = (T)(v != T(0));
+        x[c] = v;
+      }
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r) {
+        const int ty = y - r;
+        if ((unsigned)ty < (unsigned)kh) {  // (uniform)
+          if (lin) {
+            const Acc kv = A::load(s_k[reversed ? (kh - 1 - ty) * kw + (kw - 1 - tx) : ty * kw + tx]);
+            if (!(skip_zero && A::is_zero(kv))) {
+#pragma unroll
+              for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(A::mul(A::load(x[c]), kv), acc[r][c]);
+            }
+          } else if (kind == MB_PRODUCT) {
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::mul(acc[r][c], A::load(x[c]));
+          } else if (kind == MB_MAX || kind == MB_MIN) {
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) m[r][c] = mx ? (x[c] > m[r][c] ? x[c] : m[r][c]) : (x[c] < m[r][c] ? x[c] : m[r][c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < SW_CX; ++c) acc[r][c] = A::add(acc[r][c], A::load(x[c]));
+          }
+        }
+      }
+    }
+  }
+  if (kind == MB_MAX || kind == MB_MIN) {
+    SW_ALL(out[r][c] = m[r][c])
+    return;
+  }
+  if (kind == MB_AVG) {
+    const Acc n = A::from_count(avg_n);
+    SW_ALL(acc[r][c] = A::div(acc[r][c], n))
+  }
+  SW_ALL(out[r][c] = A::store(acc[r][c]))
+#undef SW_ALL
 }
 
 template <typename T, bool TMA, bool CANON>
@@ -277,8 +351,23 @@ smallwin_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // every step updates its slot in place.  8-byte elements go two rows at a time to stay within 128 registers.
     constexpr int RP = sizeof(T) == 8 ? 2 : 4;
     const T *base = sm + (warp * SW_RY) * pitch + lane;
+    if (P.dense) {
+      T vd[SW_RY][SW_CX];
+      sw_dense<T, CANON>(P.X.term_kind[0], P.kh, P.kw, P.dense == 2, P.X.term_avg_n[0], s_k, base + P.xoff, pitch, skip, vd);
+#pragma unroll
+      for (int r = 0; r < SW_RY; ++r) {
+        const int gy = oy0 + warp * SW_RY + r;
+        if (gy < P.o1) {
+#pragma unroll
+          for (int c = 0; c < SW_CX; ++c) {
+            const int gx = ox0 + lane + 32 * c;
+            if (gx < P.out_w) out[(size_t)gy * P.out_w + gx] = vd[r][c];
+          }
+        }
+      }
+    }
 #pragma unroll 1
-    for (int r0 = 0; r0 < SW_RY; r0 += RP) {
+    for (int r0 = P.dense ? SW_RY : 0; r0 < SW_RY; r0 += RP) {
       const T *rbase = base + r0 * pitch;
       T va[RP][SW_CX], vb[RP][SW_CX];
 #define SW_EACH(BODY)                      \
@@ -516,6 +605,26 @@ static int launch_sw_t(Ctx *c, const DevPlan &dp, const SWProgram &X, const void
   P.bool_canon = p.elem == MB_BOOL32;
   P.skip_zero = (p.flags & MB_FLAG_ASSUME_FINITE) != 0;
   P.trivial = X.n_terms == 1 && X.n_prog == 1;
+  // a dense window walked in (reversed) row-major order?  rank 2, one term, no program, at least three rows (below
+  // that nothing is shared between the thread's output rows)
+  P.dense = 0;
+  // Where it pays (scripts/probe_dense.py, 16384^2, Gcells/s dense vs tap list): 8-byte elements always (the tap-list
+  // form works on two rows at a time there: sum 9x9 Double 109 vs 52, conv 9x9 56 vs 48, sum 3x11 169 vs 120); sums and
+  // products over seven or more rows (sum 9x9 Word8 / Float: see DESIGN.md); not the 4-byte multiply-add kernels
+  // (conv 9x9 Float 52 vs 93: the per-row coefficient fetch costs more than the shared loads save) nor short windows.
+  const bool dense_pays = sizeof(T) == 8 || ((p.kind == MB_SUM || p.kind == MB_AVG || p.kind == MB_PRODUCT) && wh >= 7);
+  if (r == 2 && P.trivial && p.kind != MB_MAG2 && p.kind != MB_ID && wh >= 3 && (int64_t)p.ntaps == (int64_t)wh * ww &&
+      (dense_pays || std::getenv("MASSIV_B200_SW_DENSE")) && !std::getenv("MASSIV_B200_SW_NO_DENSE")) {
+    bool asc = true, desc = true;
+    for (int t = 0; t < (int)p.ntaps; ++t) {
+      const int dy = (int)(p.tap_off[2 * t] - p.min_off[0]), dx = (int)(p.tap_off[2 * t + 1] - p.min_off[1]);
+      const int ty = t / ww, tx = t % ww;
+      if (dy != ty || dx != tx) asc = false;
+      if (dy != wh - 1 - ty || dx != ww - 1 - tx) desc = false;
+    }
+    P.dense = asc ? 1 : (desc ? 2 : 0);
+    P.kh = wh; P.kw = ww;
+  }
   P.taps = (const int32_t *)d_taps2;
   P.coef = d_coef;
   P.X = X;

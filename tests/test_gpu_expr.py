@@ -121,3 +121,36 @@ def test_small_window_kernel_rank3(dev, dtname):
             want, _ = oracle_of_dw(M.mapStencil(M.Edge, cases[0] if dt.kind != "f" else cases[-1], want), want)
         got = M.iterateStencil(3, M.Edge, cases[0] if dt.kind != "f" else cases[-1], dev.fromHost(arr)).toHost()
         assert bits_equal(got, want)
+
+
+@pytest.mark.parametrize("dtname", ["float64", "int64", "float32", "uint8", "int16"])
+def test_dense_windows_share_their_loads_between_output_rows(dev, dtname):
+    """Dense windows of 8-byte elements, and tall sums / products of any type, take the small-window kernel's dense form
+    (k_smallwin.cu: sw_dense): box rows are visited once and every element is applied to all the thread's output rows
+    it belongs to — walked top-down for folds / correlations, bottom-up for convolutions (whose taps run in reverse).
+    The bits must be those of the tap-list form and of the oracle."""
+    dt = np.dtype(dtname)
+    rng = np.random.default_rng(zlib.crc32(("dense" + dtname).encode()))
+    dev.set_option("force_generic", 0)
+    dev.set_option("tile_min_elems", 0)
+    shape = (150, 333)
+    arr = (rng.standard_normal(shape) if dt.kind == "f" else rng.integers(-9 if dt.kind == "i" else 0, 10, shape)).astype(dt)
+
+    def kern(h, w):
+        return (rng.standard_normal((h, w)) if dt.kind == "f" else rng.integers(-2 if dt.kind == "i" else 0, 3, (h, w))).astype(dt)
+
+    cases = [M.sumStencil(M.Sz(9, 9)), M.sumStencil(M.Sz(7, 2)), M.productStencil(M.Sz(8, 3)), M.makeConvolutionStencilFromKernel(kern(9, 4)),
+             M.makeCorrelationStencilFromKernel(kern(4, 6)), M.makeConvolutionStencilFromKernel(kern(3, 16)), M.sumStencil(M.Sz(16, 2))]
+    if dt.kind == "f":
+        cases.append(M.avgStencil(M.Sz(11, 11)))
+    else:
+        cases += [M.maxStencil(M.Sz(3, 5)), M.minStencil(M.Sz(10, 2))]
+    try:
+        for i, st in enumerate(cases):
+            for border in (M.Edge, M.Fill(dt.type(1)), M.Wrap, M.Reflect):
+                want, _ = oracle_of_dw(M.mapStencil(border, st, arr), arr)
+                got = M.compute(M.mapStencil(border, st, dev.fromHost(arr))).toHost()
+                assert dev.last_kernel == "smallwin", (dev.last_kernel, i)
+                assert bits_equal(got, want), (i, border)
+    finally:
+        dev.set_option("tile_min_elems", 16384)
