@@ -108,8 +108,14 @@ template <typename T, int NVV> __device__ __forceinline__ void load_row(T (&dst)
 // Compile-time integer coefficients for well-known kernels (KC != void): a tap with coefficient 1 or -1
 // is one add (x * 1 is x exactly), a zero coefficient is one exact fused multiply-add fma(x, 0, acc) —
 // x*0 is exactly +-0 or NaN, so the fused and the unfused forms round identically — or nothing at all
-// when the caller promised finite inputs (FIN); everything else is the reference's multiply then add.
-template <typename T, bool FIN> __device__ __forceinline__ T tap_known(T x, T acc, int kv) {
+// when the caller promised finite inputs (FIN = 1) or the launch checks its results (FIN = 2, below); everything else is
+// the reference's multiply then add.
+// FIN = 2, the checked optimistic form (no promise needed): zero taps are skipped, every stored result is inspected,
+// and a non-finite one raises `flag`; the strict launch (FIN = 0) that follows on the stream returns at once while the
+// flag is clear.  Sound because a non-finite input that sits on a zero tap of one output sits on a non-zero tap of a
+// neighbouring output (the host checks the coefficient pattern and the geometry: known_optimistic_ok), so whenever the
+// two forms could differ somewhere, some result is non-finite.
+template <typename T, int FIN> __device__ __forceinline__ T tap_known(T x, T acc, int kv) {
   using A = Arith<T>;
   if (kv == 0) {
     if (FIN) return acc;
@@ -124,14 +130,17 @@ template <typename T, bool FIN> __device__ __forceinline__ T tap_known(T x, T ac
 // and boxes inside the array are staged with cp.async — a separate instantiation, so that the TMA
 // variant's register allocation is not disturbed (the 7x7 Float kernel sits at the 128-register limit).
 // (register staging holds a box in registers: small kernels are kept at 80 registers so that three CTAs share an SM)
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false, bool TMA = true>
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, int FIN = 0, bool TMA = true>
 #ifndef MB_T2_MINB8
 #define MB_T2_MINB8 2  // (experiment: minimum CTAs per SM of the small 8-byte kernels)
 #endif
 __global__ void __launch_bounds__(256, (!TMA && T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>::REGSTAGE && KH * KW <= 9) ? 3
                                        : (sizeof(T) == 8 && KH * KW <= 9) ? MB_T2_MINB8 : 2)
 tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const Coef<T, KH * KW> K,
-              const T *__restrict__ in, T *__restrict__ out) {
+              const T *__restrict__ in, T *__restrict__ out, unsigned *flag) {
+  // FIN = 0 with a flag: the strict redo of a checked optimistic launch — nothing to do unless that one met Inf / NaN
+  if (FIN == 0 && flag != nullptr && *reinterpret_cast<const volatile unsigned *>(flag) == 0u) return;
+  unsigned bad = 0;  // FIN = 2: running maximum of the results' exponent-and-up bits
   using C = T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>;
   using A = Arith<T>;
   using Acc = typename A::Acc;
@@ -332,6 +341,14 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
       }
       const int gy = oy0 + ly + r, gx = ox0 + lx;
       if (gy < P.y1 && gx < P.out_w) {
+        if (FIN == 2) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            unsigned hi;
+            if constexpr (sizeof(T) == 8) hi = (unsigned)__double2hiint((double)res[v]); else hi = __float_as_uint((float)res[v]);
+            if (gx + v < P.out_w) bad = max(bad, hi & 0x7fffffffu);
+          }
+        }
         T *dst = out + (size_t)gy * P.out_w + gx;
         if (P.vec_store && gx + V <= P.out_w) {
           uint4 q;
@@ -348,13 +365,15 @@ tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const T2Params P, const 
     if (!by_tma) fence_proxy_async();
     __syncthreads();  // everyone is done with stage s before it is refilled
   }
+  if (FIN == 2 && bad >= (sizeof(T) == 8 ? 0x7ff00000u : 0x7f800000u)) atomicOr(flag, 1u);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
 
 // one launch with the tile geometry of the TMA (tmap != nullptr) or the non-TMA instantiation
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC, bool FIN, bool TMA>
-static int launch_cfg(Ctx *c, const DevPlan &dp, const CUtensorMap &tmap, const void *d_in, void *d_out, const OuterRange *range) {
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC, int FIN, bool TMA>
+static int launch_cfg(Ctx *c, const DevPlan &dp, const CUtensorMap &tmap, const void *d_in, void *d_out, const OuterRange *range,
+                      unsigned *flag) {
   using C = T2Cfg<T, OP, REV, KH, KW, XOFF, TMA>;
   const Plan &p = dp.p;
   T2Params P;
@@ -394,22 +413,22 @@ static int launch_cfg(Ctx *c, const DevPlan &dp, const CUtensorMap &tmap, const 
   }
   int grid = c->num_sms * occ;
   if (grid > P.ntiles) grid = P.ntiles;
-  kern<<<grid, 256, smem_bytes, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out);
+  kern<<<grid, 256, smem_bytes, c->stream>>>(tmap, P, K, (const T *)d_in, (T *)d_out, flag);
   c->launches++;
   c->last_kernel = std::is_void<KC>::value ? "tile2d" : "tile2d_known";
   return check_cuda(c, cudaGetLastError(), "tile2d_kernel launch");
 }
 
-template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, bool FIN = false>
-static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range) {
+template <typename T, int OP, bool REV, int KH, int KW, int XOFF, typename KC = void, int FIN = 0>
+static int launch_x(Ctx *c, const DevPlan &dp, const void *d_in, void *d_out, const OuterRange *range, unsigned *flag = nullptr) {
   using CT = T2Cfg<T, OP, REV, KH, KW, XOFF, true>;
   const Plan &p = dp.p;
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
   const uint32_t box[2] = {(uint32_t)CT::BH, (uint32_t)CT::BW};
   if (!c->no_tma && make_tensor_map(&tmap, p.elem, p.esize, 2, d_in, p.in_dims, box))
-    return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, true>(c, dp, tmap, d_in, d_out, range);
-  return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, false>(c, dp, tmap, d_in, d_out, range);
+    return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, true>(c, dp, tmap, d_in, d_out, range, flag);
+  return launch_cfg<T, OP, REV, KH, KW, XOFF, KC, FIN, false>(c, dp, tmap, d_in, d_out, range, flag);
 }
 
 // well-known 3x3 kernels with compile-time coefficients (k_tile2d_known.cu); -1 when none matches

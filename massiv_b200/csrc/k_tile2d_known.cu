@@ -43,6 +43,30 @@ static bool matches(const Plan &p, bool two) {
   return true;
 }
 
+// May zero taps be skipped WITHOUT the caller's promise, with a check of the results (k_tile2d.cuh, FIN = 2)?
+// The two forms differ only where a non-finite input sits on a zero tap (0 * Inf = NaN).  Under mapStencil's geometry
+// every input cell (y, x) is window position (1 - dy, 1 - dx) (mirrored for a convolution) of output (y + dy, x + dx);
+// in an array of at least 3 x 3 cells the outputs with dy in {0, sy}, dx in {0, sx} exist for some pair of signs, so
+// the cell is seen at the centre, at one horizontal, one vertical and one diagonal neighbour position.  If in every
+// such quadrant one of these four coefficients (of either kernel of a magnitude pair) is non-zero, a non-finite cell
+// makes some result non-finite — and that is what the launch looks for.  The whole array in one launch (no row
+// ranges), Fill elements finite.
+template <typename T, typename KC>
+static bool known_optimistic_ok(Ctx *c, const Plan &p, const OuterRange *r) {
+  if (c->no_optimistic || r != nullptr || !p.same_shape() || p.in_dims[0] < 3 || p.in_dims[1] < 3) return false;
+  if (p.shift[0] + p.min_off[0] != -1 || p.shift[1] + p.min_off[1] != -1) return false;
+  if (p.border == MB_FILL) {
+    T fv;
+    std::memcpy(&fv, p.fill, sizeof(T));
+    if (!(fv - fv == T(0))) return false;
+  }
+  auto nz = [](int ry, int cx) { return KC::k1(ry * 3 + cx) != 0 || KC::k2(ry * 3 + cx) != 0; };
+  for (int ry = 0; ry <= 2; ry += 2)
+    for (int cx = 0; cx <= 2; cx += 2)
+      if (!(nz(1, 1) || nz(1, cx) || nz(ry, 1) || nz(ry, cx))) return false;
+  return true;
+}
+
 // centred 3x3 under mapStencil only (XOFF = the natural offset); everything else is generic
 template <typename T, int OP, typename KC>
 static int launch_kc(Ctx *c, const DevPlan &dp, const void *i, void *o, const OuterRange *r, bool rev) {
@@ -51,8 +75,16 @@ static int launch_kc(Ctx *c, const DevPlan &dp, const void *i, void *o, const Ou
   const int sx = (int)(dp.p.shift[1] + dp.p.min_off[1]);
   if ((((sx % V) + V) % V) != NAT) return -1;
   const bool fin = (dp.p.flags & MB_FLAG_ASSUME_FINITE) != 0;
-  if (rev) return fin ? launch_x<T, OP, true, 3, 3, NAT, KC, true>(c, dp, i, o, r) : launch_x<T, OP, true, 3, 3, NAT, KC, false>(c, dp, i, o, r);
-  return fin ? launch_x<T, OP, false, 3, 3, NAT, KC, true>(c, dp, i, o, r) : launch_x<T, OP, false, 3, 3, NAT, KC, false>(c, dp, i, o, r);
+  if (!fin && known_optimistic_ok<T, KC>(c, dp.p, r) && ensure_flag(c) == MB_OK) {
+    // optimistic launch that inspects its results, then the strict one, which only works if the flag went up
+    MB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned), c->stream));
+    int st = rev ? launch_x<T, OP, true, 3, 3, NAT, KC, 2>(c, dp, i, o, r, c->d_flag) : launch_x<T, OP, false, 3, 3, NAT, KC, 2>(c, dp, i, o, r, c->d_flag);
+    if (st) return st;
+    c->aux_launches++;
+    return rev ? launch_x<T, OP, true, 3, 3, NAT, KC, 0>(c, dp, i, o, r, c->d_flag) : launch_x<T, OP, false, 3, 3, NAT, KC, 0>(c, dp, i, o, r, c->d_flag);
+  }
+  if (rev) return fin ? launch_x<T, OP, true, 3, 3, NAT, KC, 1>(c, dp, i, o, r) : launch_x<T, OP, true, 3, 3, NAT, KC, 0>(c, dp, i, o, r);
+  return fin ? launch_x<T, OP, false, 3, 3, NAT, KC, 1>(c, dp, i, o, r) : launch_x<T, OP, false, 3, 3, NAT, KC, 0>(c, dp, i, o, r);
 }
 
 template <typename T>

@@ -93,3 +93,34 @@ def test_known_equals_generic_coefficient_path(dev):
     got = product_apply("mag2", a, resident=True, size=(3, 3), coeffs=k, coeffs2=SOBEL_Y, border="reflect")
     assert dev.last_kernel == "tile2d"
     assert bits_equal(got, O.apply("mag2", a, size=(3, 3), coeffs=k, coeffs2=SOBEL_Y, border="reflect"))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_checked_optimistic_form_one_nonfinite_cell_anywhere(dtype, dev):
+    """Without the finite promise the known kernels skip their zero taps and inspect their results; the strict launch
+    that follows only works when something non-finite showed (k_tile2d_known.cu: known_optimistic_ok).  ONE Inf or NaN
+    at every kind of position — corners, edges, interior — must give the strict result for every kernel, both
+    directions and all borders, down to the smallest arrays the optimistic form accepts (and below, where the strict
+    kernel runs alone)."""
+    rng = np.random.default_rng(99)
+    lin = [("conv", SOBEL_X), ("corr", SOBEL_X), ("conv", SOBEL_Y), ("corr", SOBEL_Y), ("conv", LAPLACE4), ("corr", PREWITT_X)]
+    mag = [(SOBEL_X, SOBEL_Y, False), (SOBEL_Y, SOBEL_X, True), (PREWITT_X, PREWITT_Y, False)]
+    for shape in ((3, 3), (3, 6), (7, 3), (40, 70), (2, 9), (9, 1)):
+        h, w = shape
+        spots = {(0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (0, w // 2), (h - 1, w // 2), (h // 2, 0), (h // 2, w - 1), (h // 2, w // 2)}
+        for (y, x) in sorted(spots):
+            a = (rng.standard_normal(shape) * 3).astype(dtype)
+            a[y, x] = rng.choice([np.inf, -np.inf, np.nan])
+            for border in BORDERS:
+                for kind, k in lin:
+                    kw = dict(size=(3, 3), coeffs=k, border=border, fill=1.5)
+                    assert bits_equal(product_apply(kind, a, resident=True, **kw), O.apply(kind, a, **kw)), (shape, y, x, border, kind, k)
+                for k1, k2, corr in mag:
+                    kw = dict(size=(3, 3), coeffs=k1, coeffs2=k2, border=border, fill=1.5)
+                    want = O.apply("mag2", a, flags=O.FLAG_MAG2_CORR if corr else 0, **kw)
+                    got = product_apply("mag2", a, flags=_abi.FLAG_MAG2_CORR if corr else 0, resident=True, **kw)
+                    assert bits_equal(got, want), (shape, y, x, border, "mag", corr)
+    # a non-finite Fill element reaches zero taps at the rim: strict kernel alone
+    a = rng.standard_normal((20, 30)).astype(dtype)
+    kw = dict(size=(3, 3), coeffs=SOBEL_X, coeffs2=SOBEL_Y, border="fill", fill=np.inf)
+    assert bits_equal(product_apply("mag2", a, resident=True, **kw), O.apply("mag2", a, **kw))
