@@ -19,7 +19,7 @@ run() {  # name  kernel-regex  skip  env  bench args...
 }
 run vol3d_tb2   vol3d_tb2        2 X=1                 --workload heat3d --steps 4
 run vol3d_star7 'vol3d_kernel'   4 MASSIV_B200_TB2=0   --workload heat3d --steps 4
-run sobel       tile2d_kernel    4 X=1                 --workload sobel --steps 4
+run sobel       tile2d_kernel    8 X=1                 --workload sobel --steps 4
 run gauss7      tile2d_kernel    4 X=1                 --workload gauss7 --steps 4
 run gauss7sep   sep2d_kernel     4 X=1                 --workload gauss7sep --steps 4
 run avg3x3      tile2d_kernel    4 X=1                 --workload avg3x3 --steps 4
