@@ -233,6 +233,15 @@ int64_t mb_aux_launch_count(mb_ctx *ctx);
 /* name of the kernel family the last launch used ("generic", "tile2d", ...); for tests/bench */
 const char *mb_last_kernel(mb_ctx *ctx);
 
+/* ---- the block schedule of mb_iterate's hidden copies (host arithmetic only; exported for tests) ----
+ * The input of `planes` outermost planes travels up in n_blocks blocks; after block k, planes
+ * [0, mb_wavefront_arrived(.., k)) are on the device.  With block k every pass q (0-based; a pass reads two planes either
+ * side of what it writes) produces output planes [*o0, *o1) (mb_wavefront_region), in the order block-major, pass-minor;
+ * afterwards planes [0, mb_wavefront_final(.., k, n_passes)) hold the final result and may leave. */
+int64_t mb_wavefront_arrived(int64_t planes, int n_blocks, int block);
+void mb_wavefront_region(int64_t planes, int n_blocks, int block, int64_t pass, int64_t *o0, int64_t *o1);
+int64_t mb_wavefront_final(int64_t planes, int n_blocks, int block, int64_t n_passes);
+
 /* ---- geometry (host only; usable without a GPU) -------------------------------------------- */
 int mb_elem_size(int elem);
 /* size arithmetic of applyStencil (Array/Stencil.hs:207-208) and strideSize (Stride.hs:102-105) */

@@ -29,7 +29,7 @@ FLAG_ASSUME_FINITE = 2
 # every symbol include/massiv_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "mb_version", "mb_status_string", "mb_ctx_create", "mb_ctx_destroy", "mb_last_error",
-    "mb_ctx_set_stream", "mb_sync", "mb_ctx_trim", "mb_ctx_set_option", "mb_launch_count", "mb_aux_launch_count", "mb_last_kernel",
+    "mb_ctx_set_stream", "mb_sync", "mb_ctx_trim", "mb_wavefront_arrived", "mb_wavefront_region", "mb_wavefront_final", "mb_ctx_set_option", "mb_launch_count", "mb_aux_launch_count", "mb_last_kernel",
     "mb_elem_size", "mb_out_dims", "mb_border_index", "mb_buf_alloc", "mb_buf_free", "mb_upload",
     "mb_download", "mb_host_alloc", "mb_host_free", "mb_run", "mb_run_dev", "mb_run_sep2_dev",
     "mb_run_sep2", "mb_iterate_dev", "mb_iterate", "mb_nccl_unique_id", "mb_shard_init",
@@ -143,6 +143,12 @@ def lib() -> C.CDLL:
     L.mb_ctx_set_stream.argtypes = [vp, vp]
     L.mb_sync.argtypes = [vp]
     L.mb_ctx_trim.argtypes = [vp]
+    L.mb_wavefront_arrived.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.mb_wavefront_arrived.restype = C.c_int64
+    L.mb_wavefront_region.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mb_wavefront_region.restype = None
+    L.mb_wavefront_final.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64]
+    L.mb_wavefront_final.restype = C.c_int64
     L.mb_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.mb_launch_count.restype = C.c_int64
     L.mb_launch_count.argtypes = [vp]

@@ -631,6 +631,27 @@ int mb_ctx_set_option(mb_ctx *h, const char *key, int64_t value) {
   return MB_OK;
 }
 
+// ---- the schedule of the wavefront (host arithmetic only; mb_wavefront_* export it for the CPU tests) ----
+// planes [0, wf_arrived(D, nb, k)) of the input have arrived once block k is up
+static int64_t wf_arrived(int64_t D, int nb, int k) { return k < 0 ? 0 : D * (int64_t)(k + 1) / nb; }
+// output planes [*o0, *o1) of pass q (0-based; every pass reads two planes either side) that become computable with block k
+static void wf_region(int64_t D, int nb, int k, int64_t q, int64_t *o0, int64_t *o1) {
+  const int64_t back = 2 * (q + 1);
+  *o0 = k == 0 ? 0 : std::max<int64_t>(0, wf_arrived(D, nb, k - 1) - back);
+  *o1 = k == nb - 1 ? D : std::max<int64_t>(0, wf_arrived(D, nb, k) - back);
+  if (*o1 < *o0) *o1 = *o0;
+}
+// planes [0, wf_final(...)) hold the result of the last of npass passes after block k's passes have run
+static int64_t wf_final(int64_t D, int nb, int k, int64_t npass) {
+  return k == nb - 1 ? D : std::max<int64_t>(0, wf_arrived(D, nb, k) - 2 * npass);
+}
+
+int64_t mb_wavefront_arrived(int64_t planes, int n_blocks, int block) { return wf_arrived(planes, n_blocks, block); }
+void mb_wavefront_region(int64_t planes, int n_blocks, int block, int64_t pass, int64_t *o0, int64_t *o1) {
+  wf_region(planes, n_blocks, block, pass, o0, o1);
+}
+int64_t mb_wavefront_final(int64_t planes, int n_blocks, int block, int64_t n_passes) { return wf_final(planes, n_blocks, block, n_passes); }
+
 int mb_ctx_trim(mb_ctx *h) {
   Guard g(h);
   if (g.st) return g.st;
@@ -890,7 +911,7 @@ static int iterate_wavefront(Ctx *c, const DevPlan *dp, const void *host_in, voi
   MB_WF(cudaStreamWaitEvent(c->out_stream, c->ev_a, 0));
   if (flag) MB_WF(cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
   const size_t rb = (size_t)p.in_dims[2] * p.esize, pb = (size_t)row_elems * p.esize;
-  auto Z = [&](int k) { return D * (k + 1) / NB; };  // planes [0, Z(k)) have arrived after block k
+  auto Z = [&](int k) { return wf_arrived(D, NB, k); };  // planes [0, Z(k)) have arrived after block k
   // uploads, in order, on the copy stream
   for (int k = 0; k < NB; ++k) {
     const int64_t z0 = k ? Z(k - 1) : 0, z1 = Z(k);
@@ -906,10 +927,8 @@ static int iterate_wavefront(Ctx *c, const DevPlan *dp, const void *host_in, voi
   for (int k = 0; k < NB; ++k) {
     MB_WF(cudaStreamWaitEvent(c->stream, c->pipe_events[k], 0));
     for (int64_t q = 0; q < npass; ++q) {
-      const int64_t back = 2 * (q + 1);
       OuterRange r;
-      r.o0 = k == 0 ? 0 : std::max<int64_t>(0, Z(k - 1) - back);
-      r.o1 = k == NB - 1 ? D : std::max<int64_t>(0, Z(k) - back);
+      wf_region(D, NB, k, q, &r.o0, &r.o1);
       if (r.o1 <= r.o0) continue;
       void *in = (q & 1) ? b : a, *out = (q & 1) ? a : b;
       int st = q < pairs ? launch_vol3d_tb2(c, p, in, out, &r, 0, 0, D, flag) : launch_plan(c, *dp, in, out, &r);
@@ -917,7 +936,7 @@ static int iterate_wavefront(Ctx *c, const DevPlan *dp, const void *host_in, voi
       if (st) return bail(st);
     }
     // the planes whose last pass is done leave while the next blocks' passes run
-    const int64_t done = k == NB - 1 ? D : std::max<int64_t>(0, Z(k) - 2 * npass);
+    const int64_t done = wf_final(D, NB, k, npass);
     if (done > sent) {
       MB_WF(cudaEventRecord(c->pipe_events[16 + k], c->stream));
       MB_WF(cudaStreamWaitEvent(c->out_stream, c->pipe_events[16 + k], 0));
