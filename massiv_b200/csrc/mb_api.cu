@@ -885,7 +885,8 @@ static int iterate_wavefront(Ctx *c, const DevPlan *dp, const void *host_in, voi
   const size_t plane_host = (size_t)p.in_dims[1] * (size_t)p.in_dims[2] * p.esize;  // ... in the caller's arrays
   if (!tb2 || pairs < 2 || D < 16 || plane_host * (size_t)D < c->wavefront_min_bytes) return -1;
   if (tb2 == 2 && ensure_flag(c) != MB_OK) return -1;
-  const int NB = 8;
+  int NB = 8;  // (measured: 4 / 8 / 16 blocks — see DESIGN.md; MASSIV_B200_WF_BLOCKS is the measurement knob)
+  if (const char *e = std::getenv("MASSIV_B200_WF_BLOCKS")) NB = std::max(2, std::min(16, std::atoi(e)));
   if (!c->out_stream && cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return -1; }
   while ((int)c->pipe_events.size() < 2 * 16) {
     cudaEvent_t e;
