@@ -388,6 +388,8 @@ class Device {
   Device &operator=(const Device &) = delete;
   mb_ctx *handle() const { return ctx_; }
   std::string lastKernel() const { return mb_last_kernel(ctx_); }
+  // gives the context's device scratch (staging arrays, padded iteration pairs) back to the driver
+  void trim() const { check(mb_ctx_trim(ctx_)); }
   void check(int st) const {
     if (!st) return;
     const char *m = mb_last_error(ctx_);
